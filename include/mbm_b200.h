@@ -1,0 +1,238 @@
+/*
+ * mbm_b200.h — C ABI of libmbm_b200.so (CUDA, sm_100a) and of oracle/libmbm_oracle.so
+ * (CPU restatement, test infrastructure only).  Both libraries export exactly the
+ * symbols declared here, with identical struct layouts, so every test can drive either.
+ *
+ * The reference (AnStroh/MovingBoundaryMinerals.jl) has no FFI seam; the seam is cut at
+ * the level of the driver main functions, whose `while t < t_tot ... end` loops
+ * (reference main_codes/<driver>.jl) are swallowed whole for a *batch* ("ensemble") of
+ * independent members.  Every entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - all arrays are caller-owned, column-major, member index = LAST dimension
+ *     (x_left[cap_left, M]: member m starts at x_left + m*cap_left);
+ *   - arrays are HOST memory unless MBM_FLAG_DEVICE_POINTERS is set, in which case every
+ *     pointer in params/io is device memory on device_ids[0] (n_devices must be 1);
+ *   - inputs are already non-dimensionalised by the host shim with the reference's own
+ *     `scaling` convention (reference src/functions.jl:988-1008);
+ *   - no exception crosses the boundary: return value 0 = call executed (inspect
+ *     status[]), <0 = library-level failure; per-member status mirrors the reference's
+ *     throw sites, a failed member is frozen and the others continue;
+ *   - re-entrant: concurrent calls from different host threads are independent.
+ */
+#ifndef MBM_B200_H
+#define MBM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBM_ABI_VERSION 2
+
+/* ---- interface condition (which `set_inner_bc_*` the step uses) -------------------- */
+enum {
+  MBM_BC_NONE           = 0, /* single phase: Simple_Diff_1D_general.jl:67-99                 */
+  MBM_BC_FLUX           = 1, /* set_inner_bc_flux!   src/functions.jl:1054-1072               */
+  MBM_BC_MB             = 2, /* set_inner_bc_mb!     src/functions.jl:1094-1109               */
+  MBM_BC_STEFAN         = 3, /* set_inner_bc_stefan! src/functionsStefan.jl:131-144           */
+  MBM_BC_DIRICHLET_HOLD = 4  /* inline rows, examples/Diff_couple_no_interaction.jl:108-118   */
+};
+
+/* ---- time-step rule ----------------------------------------------------------------- */
+enum {
+  MBM_DT_FIND_DT   = 0, /* find_dt, src/functions.jl:465-490                                  */
+  MBM_DT_ADVECTIVE = 1, /* dt = minimum([dx1,dx2])/V_ip*CFL, examples/C1.jl:93, B4.jl:93      */
+  MBM_DT_STEFAN    = 2, /* Chemical_Stefan_problem_XT.jl:79,147-149 (dt carried in io.dt)     */
+  MBM_DT_SIMPLE    = 3  /* calculate_dt, src/functions.jl:164-168                             */
+};
+
+/* ---- flags ---------------------------------------------------------------------------- */
+#define MBM_FLAG_NEWTON_WARM      0x0001u /* start newton_solver from the previous root instead of 1.1
+                                             (reference cold-starts every regrid: functions.jl:734)      */
+#define MBM_FLAG_RECORD           0x0002u /* fill io.rec (per-step Mass/T/KD/Ri history)                 */
+#define MBM_FLAG_SOLVER_FAITHFUL  0x0004u /* ORACLE ONLY: dense partial-pivot LU like `L_g \ R_g`
+                                             (functions.jl:1292) instead of the O(N) structured solve   */
+#define MBM_FLAG_SUM_JULIA        0x0008u /* ORACLE ONLY: Julia-like pairwise cumsum + sequential
+                                             make_dx_right instead of the canonical order shared with
+                                             the CUDA kernels ("canonical summation order")   */
+#define MBM_FLAG_DEVICE_POINTERS  0x0010u /* CUDA ONLY: params/io arrays are device pointers             */
+#define MBM_FLAG_FORCE_RESIDENT   0x0020u /* CUDA ONLY: force the shared-memory resident kernel          */
+#define MBM_FLAG_FORCE_STREAMING  0x0040u /* CUDA ONLY: force the global-memory kernel                   */
+#define MBM_FLAG_MASS_FINAL       0x0080u /* compute io.Mass after the last executed step
+                                             (calc_mass_vol, functions.jl:205-212)                       */
+
+/* ---- per-member status (mirrors the reference's error() sites) ---------------------- */
+enum {
+  MBM_OK                    = 0,
+  MBM_ERR_IFACE_FAST_POS    = 1,  /* functions.jl:39  "Ri is larger than x_right[2]"          */
+  MBM_ERR_IFACE_FAST_NEG    = 2,  /* functions.jl:52  "Ri is smaller than x_left[end-1]"      */
+  MBM_ERR_NEWTON            = 3,  /* functions.jl:752 "Newton Failure"                        */
+  MBM_ERR_KD_RANGE          = 4,  /* functions.jl:1362                                        */
+  MBM_ERR_T_RANGE           = 5,  /* functions.jl:1365, :1412                                 */
+  MBM_ERR_INTERP_BOUNDS     = 6,  /* functions.jl:571                                         */
+  MBM_ERR_NDIM              = 7,  /* functions.jl:513                                         */
+  MBM_ERR_PCHIP_INDEX       = 8,  /* functions.jl:822                                         */
+  MBM_ERR_DENSITY_BOUNDS    = 9,  /* functionsStefan.jl:97-98                                 */
+  MBM_ERR_CAPACITY          = 10, /* node count would exceed cap_left / cap_right             */
+  MBM_ERR_NONFINITE         = 11, /* NaN/Inf in the state                                     */
+  MBM_ERR_MREFIN            = 12  /* MRefin < 1 branch (functions.jl:412-426) is unsupported  */
+};
+#define MBM_WARN_NEWTON_RES 0x1   /* Newton residual in (1e-8, 1e-3] after 200 its, functions.jl:754 */
+
+/* library-level return codes */
+enum {
+  MBM_RC_OK = 0, MBM_RC_BAD_ARG = -1, MBM_RC_CUDA = -2, MBM_RC_OOM = -3, MBM_RC_UNSUPPORTED = -4,
+  MBM_RC_NO_DEVICE = -5
+};
+
+/* ---- argument blocks -------------------------------------------------------------------- */
+
+/* replaces the "Numerics"/"Physics" literals at the top of every driver main function,
+ * e.g. main_codes/Diff_couple_1D_general_MB.jl:7-33                                          */
+typedef struct mbm_common {
+  int32_t abi_version;   /* MBM_ABI_VERSION                                                   */
+  int32_t n_members;     /* M                                                                 */
+  int32_t ndim;          /* `n`: 1 planar, 2 cylindrical, 3 spherical                         */
+  int32_t hist_len;      /* length of t_ar / T_ar / KD_ar (Stefan: tpath / Tpath)             */
+  int32_t cap_left;      /* leading dimension of x_left/C_left (>= res[1]+1)                  */
+  int32_t cap_right;     /* leading dimension of x_right/C_right (>= res[2]+1); 0 for simple  */
+  int32_t inner_bc;      /* MBM_BC_*                                                          */
+  int32_t dt_mode;       /* MBM_DT_*                                                          */
+  uint32_t flags;        /* MBM_FLAG_*                                                        */
+  int32_t n_devices;     /* CUDA: number of GPUs to shard members over (contiguous blocks)    */
+  int64_t max_steps;     /* 0 = run every member to t_tot; else at most this many steps/call  */
+  const int32_t *device_ids; /* [n_devices] or NULL = 0..n_devices-1                          */
+  int64_t rec_cap;       /* leading dimension of io.rec (steps recorded per member)           */
+} mbm_common;
+
+/* Diff_couple_1D_general_{MB,Flux}.jl:7-33 and Chemical_Stefan_problem_XT.jl:8-26, one
+ * column per member.  A member stride of 0 means "one array shared by all members".        */
+typedef struct mbm_couple_params {
+  const double *Di;      /* [2,M] scaled; Di == [-1 -1] selects Arrhenius (functions.jl:1368) */
+  const double *D0;      /* [2,M]                                                             */
+  const double *Ea;      /* [2,M] Ea1, Ea2                                                    */
+  const double *rho;     /* [2,M]                                                             */
+  const double *V_ip;    /* [M]   (ignored for MBM_BC_STEFAN: computed from the fluxes)       */
+  const double *t_tot;   /* [M]                                                               */
+  const double *CFL;     /* [M]                                                               */
+  const double *MRefin;  /* [M]                                                               */
+  const int32_t *BCout;  /* [2,M] 1 = Dirichlet, 0 = Neumann                                  */
+  const int64_t *resmin; /* [2,M]                                                             */
+  const double *t_ar;    /* [hist_len, M or 1]                                                */
+  const double *T_ar;    /* [hist_len, M or 1]                                                */
+  const double *KD_ar;   /* [hist_len, M or 1] (unused for Stefan)                            */
+  int64_t t_stride, T_stride, KD_stride; /* elements between members; 0 = shared             */
+  double R;              /* gas constant                                                      */
+  /* --- Stefan only (NULL otherwise) --- */
+  const double *coeff_up;   /* [3,M or 1] composition(): X_right(T), functionsStefan.jl:69    */
+  const double *coeff_do;   /* [3,M or 1] composition(): X_left(T),  functionsStefan.jl:68    */
+  int64_t coeff_stride;     /* 0 = shared                                                     */
+  const double *C_leftB;    /* [M] initial equilibrium compositions used by calculate_density */
+  const double *C_rightB;   /* [M]                                                            */
+  int32_t nd;               /* density table is nd x nd; 0 = no table, rho stays params.rho   */
+  int32_t reserved;
+  const double *dens_X;     /* [nd]     Xwm[:,1]                                              */
+  const double *dens_T;     /* [nd]     Twm[1,:]                                              */
+  const double *dens_left;  /* [nd,nd]  column-major                                          */
+  const double *dens_right; /* [nd,nd]                                                        */
+} mbm_couple_params;
+
+/* in/out state of a couple ensemble; calling again with the returned state resumes the run
+ * (the reference keeps this state in local variables of the driver function).               */
+typedef struct mbm_couple_io {
+  double  *x_left;   /* [cap_left,  M]                                                        */
+  double  *C_left;   /* [cap_left,  M]                                                        */
+  double  *x_right;  /* [cap_right, M]                                                        */
+  double  *C_right;  /* [cap_right, M]                                                        */
+  int64_t *res;      /* [2,M] node counts (reference mutates `res`, functions.jl:44,57,874)   */
+  double  *Ri;       /* [2,M] (reference mutates Ri[1], functions.jl:31)                      */
+  double  *t;        /* [M]                                                                   */
+  double  *dt;       /* [M] last dt; for MBM_DT_STEFAN the dt of the next step (in/out)       */
+  int64_t *it;       /* [M] step counter                                                      */
+  double  *dx1;      /* [M] out                                                               */
+  double  *dx2;      /* [M] out                                                               */
+  double  *Mass0;    /* [M] in  (calc_mass_vol at t = 0, e.g. ..._MB.jl:62)                   */
+  double  *Mass;     /* [M] out (MBM_FLAG_MASS_FINAL) or NULL                                 */
+  double  *newton_R; /* [M] in/out last geometric ratio (0 = none yet) or NULL                */
+  double  *last;     /* [8,M] out: D_l, D_r, KD, T, V_ip, rho1, rho2, Fl_regrid; or NULL      */
+  int32_t *status;   /* [M] in/out: members with status != 0 on entry are skipped             */
+  int32_t *warn;     /* [M] out bitmask                                                       */
+  uint64_t *idx_hash;/* [M] in/out order-independent checksum of every regrid interval index
+                              and pchip branch taken so far, or NULL                          */
+  int64_t *node_steps;/*[M] in/out sum over executed steps of the node count solved           */
+  double  *rec;      /* [4, rec_cap, M] per-step (Mass, T, KD, Ri[1]) if MBM_FLAG_RECORD      */
+} mbm_couple_io;
+
+/* Simple_Diff_1D_general.jl:6-31 */
+typedef struct mbm_simple_params {
+  const double *Di;     /* [M]; -1 selects Arrhenius (functions.jl:1415)                      */
+  const double *D0;     /* [M]                                                                */
+  const double *Ea1;    /* [M]                                                                */
+  const double *rho;    /* [M]                                                                */
+  const double *dx;     /* [M] spacing used by calculate_dt (L*inv(res-1.0))                  */
+  const double *t_tot;  /* [M]                                                                */
+  const double *CFL;    /* [M]                                                                */
+  const int32_t *BCout; /* [2,M]                                                              */
+  const double *t_ar;   /* [hist_len, M or 1]                                                 */
+  const double *T_ar;   /* [hist_len, M or 1]                                                 */
+  int64_t t_stride, T_stride;
+  double R;
+} mbm_simple_params;
+
+typedef struct mbm_simple_io {
+  double  *x;        /* [cap_left, M] (fixed mesh)                                            */
+  double  *C;        /* [cap_left, M]                                                         */
+  int64_t *res;      /* [M]                                                                   */
+  double  *t;        /* [M]                                                                   */
+  double  *dt;       /* [M]                                                                   */
+  int64_t *it;       /* [M]                                                                   */
+  double  *D;        /* [M] out: last diffusivity                                             */
+  double  *Mass;     /* [M] out (MBM_FLAG_MASS_FINAL; calc_mass_vol_simple_diff) or NULL      */
+  int32_t *status;   /* [M]                                                                   */
+  int64_t *node_steps;/*[M]                                                                   */
+} mbm_simple_io;
+
+/* ---- entry points ------------------------------------------------------------------------ */
+int mbm_version(void);
+int mbm_device_count(void);          /* oracle: 0                                             */
+const char *mbm_backend(void);       /* "cuda-sm_100a" or "oracle-cpu"                        */
+const char *mbm_status_string(int32_t status);
+
+/* SDG(): main_codes/Simple_Diff_1D_general.jl:4-103 (also examples/A1.jl, A2.jl)             */
+int mbm_simple_diff_batch(const mbm_common *, const mbm_simple_params *, mbm_simple_io *);
+/* DCGF(): main_codes/Diff_couple_1D_general_Flux.jl:4-138 (B1..B7);
+ * with inner_bc = MBM_BC_DIRICHLET_HOLD also DCNI(), examples/Diff_couple_no_interaction.jl  */
+int mbm_couple_flux_batch(const mbm_common *, const mbm_couple_params *, mbm_couple_io *);
+/* DCGMB(): main_codes/Diff_couple_1D_general_MB.jl:4-140 (C1, C2, Diff_couple_MB_growth)     */
+int mbm_couple_mb_batch(const mbm_common *, const mbm_couple_params *, mbm_couple_io *);
+/* CSP(): main_codes/Chemical_Stefan_problem_XT.jl:4-208 (D1)                                 */
+int mbm_stefan_xt_batch(const mbm_common *, const mbm_couple_params *, mbm_couple_io *);
+/* generic form of the three couple entry points: inner_bc taken from common                 */
+int mbm_couple_batch(const mbm_common *, const mbm_couple_params *, mbm_couple_io *);
+
+/* pre-loop helpers of the drivers, batched (host side of both libraries is plain CPU code;
+ * they run once per run and are not on the hot path):
+ * create_grid!: functions.jl:364-370 -> define_new_grid :395-441                             */
+int mbm_create_grid(int32_t n_members, int32_t cap_left, int32_t cap_right,
+                    const double *Ri /*[2,M]*/, const int64_t *res /*[2,M]*/,
+                    const double *MRefin /*[M]*/, double *x_left, double *x_right,
+                    double *dx1, double *dx2, double *newton_R /*[M] or NULL*/,
+                    int32_t *status /*[M]*/);
+/* calc_mass_vol: functions.jl:205-212 */
+int mbm_calc_mass_vol(int32_t n_members, int32_t ndim, int32_t cap_left, int32_t cap_right,
+                      const double *x_left, const double *x_right, const double *C_left,
+                      const double *C_right, const int64_t *res, const double *rho,
+                      double *Mass /*[M]*/);
+
+/* CUDA library only: seconds spent in the last call's kernels on device_ids[0], measured
+ * with CUDA events on the launching stream (0 for the oracle), and the number of kernel
+ * launches of the last call.                                                               */
+double mbm_last_kernel_seconds(void);
+int64_t mbm_last_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBM_B200_H */
