@@ -1,0 +1,461 @@
+// mbm_api.cu — C ABI of libmbm_b200.so (include/mbm_b200.h): argument checking, host<->device staging,
+// member sharding over GPUs (contiguous blocks, no collective: members never communicate), kernel
+// dispatch.  There is no CPU compute path in this library: without a CUDA device every entry point
+// returns MBM_RC_NO_DEVICE.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../include/mbm_b200.h"
+#include "mbm_kernels.cuh"
+
+namespace {
+
+thread_local double g_last_kernel_seconds = 0.0;
+thread_local long long g_last_kernel_launches = 0;
+double g_last_kernel_seconds_any = 0.0;
+long long g_last_kernel_launches_any = 0;
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      fprintf(stderr, "[mbm_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__,   \
+              __LINE__, cudaGetErrorString(e_));                                                   \
+      return (e_ == cudaErrorMemoryAllocation) ? MBM_RC_OOM : MBM_RC_CUDA;                         \
+    }                                                                                              \
+  } while (0)
+
+// staging of one shard: device copies of host arrays, copied back on request
+struct Stage {
+  struct Item { void *h; void *d; size_t bytes; bool out; };
+  std::vector<Item> items;
+  std::vector<void *> owned;
+  cudaStream_t stream = nullptr;
+  bool device_ptrs = false;
+  int rc = 0;
+
+  template <typename Tp>
+  Tp *in(const Tp *h, size_t count, bool out = false) {
+    if (!h || count == 0) return nullptr;
+    if (device_ptrs) return const_cast<Tp *>(h);
+    void *d = nullptr;
+    cudaError_t e = cudaMallocAsync(&d, count * sizeof(Tp), stream);
+    if (e != cudaSuccess) { rc = (e == cudaErrorMemoryAllocation) ? MBM_RC_OOM : MBM_RC_CUDA; return nullptr; }
+    owned.push_back(d);
+    e = cudaMemcpyAsync(d, h, count * sizeof(Tp), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) { rc = MBM_RC_CUDA; return nullptr; }
+    items.push_back({(void *)h, d, count * sizeof(Tp), out});
+    return (Tp *)d;
+  }
+  template <typename Tp>
+  Tp *inout(Tp *h, size_t count) { return in<Tp>(h, count, true); }
+  template <typename Tp>
+  Tp *outonly(Tp *h, size_t count) {
+    if (!h || count == 0) return nullptr;
+    if (device_ptrs) return h;
+    void *d = nullptr;
+    cudaError_t e = cudaMallocAsync(&d, count * sizeof(Tp), stream);
+    if (e != cudaSuccess) { rc = (e == cudaErrorMemoryAllocation) ? MBM_RC_OOM : MBM_RC_CUDA; return nullptr; }
+    owned.push_back(d);
+    cudaMemsetAsync(d, 0, count * sizeof(Tp), stream);
+    items.push_back({(void *)h, d, count * sizeof(Tp), true});
+    return (Tp *)d;
+  }
+  void *scratch(size_t bytes) {
+    void *d = nullptr;
+    cudaError_t e = cudaMallocAsync(&d, bytes, stream);
+    if (e != cudaSuccess) { rc = (e == cudaErrorMemoryAllocation) ? MBM_RC_OOM : MBM_RC_CUDA; return nullptr; }
+    owned.push_back(d);
+    return d;
+  }
+  int copy_back() {
+    for (auto &it : items)
+      if (it.out) {
+        cudaError_t e = cudaMemcpyAsync(it.h, it.d, it.bytes, cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return MBM_RC_CUDA;
+      }
+    return 0;
+  }
+  void release() {
+    for (void *p : owned) cudaFreeAsync(p, stream);
+    owned.clear();
+    items.clear();
+  }
+};
+
+int threads_for(int capS) {
+  if (const char *e = getenv("MBM_THREADS")) {
+    int t = atoi(e);
+    if (t == 32 || t == 64 || t == 128 || t == 256 || t == 512) return t;
+  }
+  if (capS <= 160) return 32;
+  if (capS <= 640) return 64;
+  if (capS <= 1600) return 128;
+  return 256;
+}
+
+template <int T>
+int launch_T(const mbm::KArgs &A, int member0, int count, bool use_global, size_t smem_bytes, cudaStream_t s) {
+  auto kern = mbm::mbm_step_kernel<T>;
+  if (!use_global) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return MBM_RC_CUDA;
+  }
+  kern<<<count, T, use_global ? 0 : smem_bytes, s>>>(A, member0);
+  return (cudaGetLastError() == cudaSuccess) ? 0 : MBM_RC_CUDA;
+}
+
+size_t static_smem_for(int T) { return sizeof(mbm::Scal) + 8 * (size_t)T * sizeof(double) + 256; }
+
+// run one shard [m0, m1) of an already device-resident KArgs
+int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaStream_t s, Stage *st,
+                 double *kernel_seconds) {
+  const int capS = A.capS;
+  const size_t per_cta = 5 * (size_t)capS + (size_t)(capS / 256 + 8);
+  const size_t dyn = per_cta * sizeof(double);
+  int T = threads_for(capS);
+  int maxOptin = 0;
+  CK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  bool use_global = (dyn + static_smem_for(T) > (size_t)maxOptin);
+  if (flags & MBM_FLAG_FORCE_STREAMING) use_global = true;
+  if ((flags & MBM_FLAG_FORCE_RESIDENT) && use_global && !(flags & MBM_FLAG_FORCE_STREAMING)) return MBM_RC_UNSUPPORTED;
+  const int count = m1 - m0;
+  if (count <= 0) return 0;
+  int chunk = count;
+  if (use_global) {
+    if (!getenv("MBM_THREADS")) T = 512;
+    // bound the workspace: at most 8 GiB, members processed in waves
+    const size_t maxws = (size_t)8 << 30;
+    size_t nmax = maxws / (per_cta * sizeof(double));
+    if (nmax < 1) nmax = 1;
+    if ((size_t)chunk > nmax) chunk = (int)nmax;
+    A.workspace = (double *)st->scratch((size_t)chunk * per_cta * sizeof(double));
+    if (!A.workspace) return st->rc ? st->rc : MBM_RC_OOM;
+  }
+  A.use_global = use_global ? 1 : 0;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, s));
+  long long launches = 0;
+  for (int off = 0; off < count; off += chunk) {
+    const int n = (count - off < chunk) ? (count - off) : chunk;
+    int rc;
+    switch (T) {
+      case 32: rc = launch_T<32>(A, m0 + off, n, use_global, dyn, s); break;
+      case 64: rc = launch_T<64>(A, m0 + off, n, use_global, dyn, s); break;
+      case 128: rc = launch_T<128>(A, m0 + off, n, use_global, dyn, s); break;
+      case 512: rc = launch_T<512>(A, m0 + off, n, use_global, dyn, s); break;
+      default: rc = launch_T<256>(A, m0 + off, n, use_global, dyn, s); break;
+    }
+    if (rc) return rc;
+    ++launches;
+  }
+  CK(cudaEventRecord(e1, s));
+  CK(cudaStreamSynchronize(s));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (kernel_seconds) *kernel_seconds = ms * 1e-3;
+  g_last_kernel_launches = launches;
+  return 0;
+}
+
+int check_common(const mbm_common *c) {
+  if (!c || c->abi_version != MBM_ABI_VERSION) return MBM_RC_BAD_ARG;
+  if (c->n_members < 0 || c->cap_left < 3 || c->hist_len < 2) return MBM_RC_BAD_ARG;
+  if (c->n_devices < 1) return MBM_RC_BAD_ARG;
+  if ((c->flags & MBM_FLAG_DEVICE_POINTERS) && c->n_devices != 1) return MBM_RC_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return MBM_RC_NO_DEVICE;
+  for (int i = 0; i < c->n_devices; ++i) {
+    const int d = c->device_ids ? c->device_ids[i] : i;
+    if (d < 0 || d >= ndev) return MBM_RC_NO_DEVICE;
+  }
+  return 0;
+}
+
+// ---- couple shard ------------------------------------------------------------------------------------
+int couple_shard(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io *io, int m0, int m1, int device,
+                 double *ksec) {
+  CK(cudaSetDevice(device));
+  Stage st;
+  st.device_ptrs = (c->flags & MBM_FLAG_DEVICE_POINTERS) != 0;
+  CK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+  const size_t n = (size_t)(m1 - m0), capL = c->cap_left, capR = c->cap_right, H = c->hist_len;
+  mbm::KArgs A;
+  memset(&A, 0, sizeof(A));
+  A.M = (int)n; A.ndim = c->ndim; A.hist_len = c->hist_len; A.capL = c->cap_left; A.capR = c->cap_right;
+  A.capS = c->cap_left + c->cap_right + 1; A.inner_bc = c->inner_bc; A.dt_mode = c->dt_mode; A.flags = c->flags;
+  A.pstride = 2; A.max_steps = c->max_steps; A.rec_cap = c->rec_cap; A.R = p->R;
+  // all arrays are re-based to the shard: member index inside the kernel is 0..n-1
+  A.Di = st.in(p->Di + 2 * (size_t)m0, 2 * n);
+  A.D0 = st.in(p->D0 ? p->D0 + 2 * (size_t)m0 : nullptr, 2 * n);
+  A.Ea = st.in(p->Ea ? p->Ea + 2 * (size_t)m0 : nullptr, 2 * n);
+  A.rho = st.in(p->rho + 2 * (size_t)m0, 2 * n);
+  A.V_ip = st.in(p->V_ip ? p->V_ip + m0 : nullptr, n);
+  A.t_tot = st.in(p->t_tot + m0, n);
+  A.CFL = st.in(p->CFL + m0, n);
+  A.MRefin = st.in(p->MRefin + m0, n);
+  A.BCout = st.in(p->BCout + 2 * (size_t)m0, 2 * n);
+  A.resmin = (const long long *)st.in(p->resmin + 2 * (size_t)m0, 2 * n);
+  A.t_stride = p->t_stride; A.T_stride = p->T_stride; A.KD_stride = p->KD_stride;
+  A.t_ar = st.in(p->t_ar + (size_t)m0 * p->t_stride, p->t_stride ? n * H : H);
+  A.T_ar = st.in(p->T_ar + (size_t)m0 * p->T_stride, p->T_stride ? n * H : H);
+  A.KD_ar = p->KD_ar ? st.in(p->KD_ar + (size_t)m0 * p->KD_stride, p->KD_stride ? n * H : H) : nullptr;
+  if (c->inner_bc == MBM_BC_STEFAN) {
+    A.coeff_stride = p->coeff_stride;
+    A.coeff_up = st.in(p->coeff_up + (size_t)m0 * p->coeff_stride, p->coeff_stride ? 3 * n : 3);
+    A.coeff_do = st.in(p->coeff_do + (size_t)m0 * p->coeff_stride, p->coeff_stride ? 3 * n : 3);
+    A.C_leftB = st.in(p->C_leftB + m0, n);
+    A.C_rightB = st.in(p->C_rightB + m0, n);
+    A.nd = p->nd;
+    if (p->nd > 0) {
+      A.dens_X = st.in(p->dens_X, (size_t)p->nd);
+      A.dens_T = st.in(p->dens_T, (size_t)p->nd);
+      A.dens_left = st.in(p->dens_left, (size_t)p->nd * p->nd);
+      A.dens_right = st.in(p->dens_right, (size_t)p->nd * p->nd);
+    }
+  }
+  A.x_left = st.inout(io->x_left + (size_t)m0 * capL, n * capL);
+  A.C_left = st.inout(io->C_left + (size_t)m0 * capL, n * capL);
+  A.x_right = st.inout(io->x_right + (size_t)m0 * capR, n * capR);
+  A.C_right = st.inout(io->C_right + (size_t)m0 * capR, n * capR);
+  A.res = (long long *)st.inout(io->res + 2 * (size_t)m0, 2 * n);
+  A.Ri = st.inout(io->Ri + 2 * (size_t)m0, 2 * n);
+  A.t = st.inout(io->t + m0, n);
+  A.dt = st.inout(io->dt + m0, n);
+  A.it = (long long *)st.inout(io->it + m0, n);
+  A.dx1 = io->dx1 ? st.outonly(io->dx1 + m0, n) : nullptr;
+  A.dx2 = io->dx2 ? st.outonly(io->dx2 + m0, n) : nullptr;
+  A.Mass0 = io->Mass0 ? st.in(io->Mass0 + m0, n) : nullptr;
+  A.Mass = io->Mass ? st.inout(io->Mass + m0, n) : nullptr;
+  A.newton_R = io->newton_R ? st.inout(io->newton_R + m0, n) : nullptr;
+  A.last = io->last ? st.inout(io->last + 8 * (size_t)m0, 8 * n) : nullptr;
+  A.status = st.inout(io->status + m0, n);
+  A.warn = io->warn ? st.inout(io->warn + m0, n) : nullptr;
+  A.idx_hash = io->idx_hash ? (unsigned long long *)st.inout(io->idx_hash + m0, n) : nullptr;
+  A.node_steps = io->node_steps ? (long long *)st.inout(io->node_steps + m0, n) : nullptr;
+  if ((c->flags & MBM_FLAG_RECORD) && io->rec && c->rec_cap > 0)
+    A.rec = st.inout(io->rec + 4 * (size_t)c->rec_cap * (size_t)m0, 4 * (size_t)c->rec_cap * n);
+  int rc = st.rc;
+  if (!rc) rc = launch_shard(A, 0, (int)n, device, c->flags, st.stream, &st, ksec);
+  if (!rc) rc = st.copy_back();
+  if (!rc && cudaStreamSynchronize(st.stream) != cudaSuccess) rc = MBM_RC_CUDA;
+  st.release();
+  cudaStreamSynchronize(st.stream);
+  cudaStreamDestroy(st.stream);
+  return rc;
+}
+
+int simple_shard(const mbm_common *c, const mbm_simple_params *p, mbm_simple_io *io, int m0, int m1, int device,
+                 double *ksec) {
+  CK(cudaSetDevice(device));
+  Stage st;
+  st.device_ptrs = (c->flags & MBM_FLAG_DEVICE_POINTERS) != 0;
+  CK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+  const size_t n = (size_t)(m1 - m0), cap = c->cap_left, H = c->hist_len;
+  mbm::KArgs A;
+  memset(&A, 0, sizeof(A));
+  A.M = (int)n; A.ndim = c->ndim; A.hist_len = c->hist_len; A.capL = c->cap_left; A.capR = 0;
+  A.capS = c->cap_left + 1; A.inner_bc = MBM_BC_NONE; A.dt_mode = MBM_DT_SIMPLE; A.flags = c->flags;
+  A.pstride = 1; A.max_steps = c->max_steps; A.R = p->R;
+  A.Di = st.in(p->Di + m0, n);
+  A.D0 = st.in(p->D0 ? p->D0 + m0 : nullptr, n);
+  A.Ea = st.in(p->Ea1 ? p->Ea1 + m0 : nullptr, n);
+  A.rho = st.in(p->rho + m0, n);
+  A.s_dx = st.in(p->dx + m0, n);
+  A.t_tot = st.in(p->t_tot + m0, n);
+  A.CFL = st.in(p->CFL + m0, n);
+  A.BCout = st.in(p->BCout + 2 * (size_t)m0, 2 * n);
+  A.t_stride = p->t_stride; A.T_stride = p->T_stride;
+  A.t_ar = st.in(p->t_ar + (size_t)m0 * p->t_stride, p->t_stride ? n * H : H);
+  A.T_ar = st.in(p->T_ar + (size_t)m0 * p->T_stride, p->T_stride ? n * H : H);
+  A.x_left = st.inout(io->x + (size_t)m0 * cap, n * cap);
+  A.C_left = st.inout(io->C + (size_t)m0 * cap, n * cap);
+  A.res = (long long *)st.inout(io->res + m0, n);
+  A.t = st.inout(io->t + m0, n);
+  A.dt = st.inout(io->dt + m0, n);
+  A.it = (long long *)st.inout(io->it + m0, n);
+  A.s_D = io->D ? st.outonly(io->D + m0, n) : nullptr;
+  A.Mass = io->Mass ? st.inout(io->Mass + m0, n) : nullptr;
+  A.status = st.inout(io->status + m0, n);
+  A.node_steps = io->node_steps ? (long long *)st.inout(io->node_steps + m0, n) : nullptr;
+  int rc = st.rc;
+  if (!rc) rc = launch_shard(A, 0, (int)n, device, c->flags, st.stream, &st, ksec);
+  if (!rc) rc = st.copy_back();
+  if (!rc && cudaStreamSynchronize(st.stream) != cudaSuccess) rc = MBM_RC_CUDA;
+  st.release();
+  cudaStreamSynchronize(st.stream);
+  cudaStreamDestroy(st.stream);
+  return rc;
+}
+
+// contiguous blocks of ceil(M/G) members per device, one host thread per device
+template <typename F>
+int run_sharded(const mbm_common *c, F shard_fn) {
+  const int G = c->n_devices, M = c->n_members;
+  if (M == 0) return 0;
+  const int per = (M + G - 1) / G;
+  std::vector<int> rcs(G, 0);
+  std::vector<double> ks(G, 0.0);
+  int prev_dev = 0;
+  cudaGetDevice(&prev_dev);
+  if (G == 1) {
+    rcs[0] = shard_fn(0, M, c->device_ids ? c->device_ids[0] : 0, &ks[0]);
+  } else {
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) {
+      const int m0 = g * per, m1 = (m0 + per < M) ? (m0 + per) : M;
+      if (m0 >= m1) continue;
+      const int dev = c->device_ids ? c->device_ids[g] : g;
+      th.emplace_back([&, g, m0, m1, dev]() { rcs[g] = shard_fn(m0, m1, dev, &ks[g]); });
+    }
+    for (auto &t : th) t.join();
+  }
+  cudaSetDevice(prev_dev);
+  g_last_kernel_seconds = ks[0];
+  g_last_kernel_seconds_any = ks[0];
+  g_last_kernel_launches_any = g_last_kernel_launches ? g_last_kernel_launches : 1;
+  for (int g = 0; g < G; ++g)
+    if (rcs[g]) return rcs[g];
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mbm_version(void) { return MBM_ABI_VERSION; }
+
+int mbm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char *mbm_backend(void) { return "cuda-sm_100a"; }
+
+double mbm_last_kernel_seconds(void) { return g_last_kernel_seconds_any; }
+int64_t mbm_last_kernel_launches(void) { return g_last_kernel_launches_any; }
+
+const char *mbm_status_string(int32_t s) {
+  switch (s) {
+    case MBM_OK: return "ok";
+    case MBM_ERR_IFACE_FAST_POS: return "Interface moved too fast. Ri is larger than x_right[2].";
+    case MBM_ERR_IFACE_FAST_NEG: return "Interface moved too fast. Ri is smaller than x_left[end-1].";
+    case MBM_ERR_NEWTON: return "Cannot proceed (Newton Failure) - increase Ri[1] or increase grid resolution.";
+    case MBM_ERR_KD_RANGE: return "KD exceeds the values of KD_ar.";
+    case MBM_ERR_T_RANGE: return "Temperature exceeds the values of T_ar.";
+    case MBM_ERR_INTERP_BOUNDS: return "x_interp is out of bounds of x.";
+    case MBM_ERR_NDIM: return "Error in geometry (n must be 1,2 or 3).";
+    case MBM_ERR_PCHIP_INDEX: return "k out of bounds";
+    case MBM_ERR_DENSITY_BOUNDS: return "Value should be within bounds to interpolate.";
+    case MBM_ERR_CAPACITY: return "node capacity exceeded";
+    case MBM_ERR_NONFINITE: return "non-finite state";
+    case MBM_ERR_MREFIN: return "MRefin < 1 is unsupported";
+    default: return "unknown status";
+  }
+}
+
+int mbm_couple_batch(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io *io) {
+  int rc = check_common(c);
+  if (rc) return rc;
+  if (!p || !io || c->cap_right < 3) return MBM_RC_BAD_ARG;
+  if (c->inner_bc < MBM_BC_FLUX || c->inner_bc > MBM_BC_DIRICHLET_HOLD) return MBM_RC_BAD_ARG;
+  if (!p->Di || !p->rho || !p->t_tot || !p->CFL || !p->MRefin || !p->BCout || !p->resmin || !p->t_ar || !p->T_ar)
+    return MBM_RC_BAD_ARG;
+  if (c->inner_bc != MBM_BC_STEFAN && !p->KD_ar) return MBM_RC_BAD_ARG;
+  if (!io->x_left || !io->C_left || !io->x_right || !io->C_right || !io->res || !io->Ri || !io->t || !io->dt ||
+      !io->it || !io->status)
+    return MBM_RC_BAD_ARG;
+  if (c->flags & (MBM_FLAG_SOLVER_FAITHFUL | MBM_FLAG_SUM_JULIA)) return MBM_RC_UNSUPPORTED;  // oracle-only modes
+  return run_sharded(c, [&](int m0, int m1, int dev, double *ks) { return couple_shard(c, p, io, m0, m1, dev, ks); });
+}
+
+int mbm_couple_flux_batch(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io *io) {
+  if (!c || (c->inner_bc != MBM_BC_FLUX && c->inner_bc != MBM_BC_DIRICHLET_HOLD)) return MBM_RC_BAD_ARG;
+  return mbm_couple_batch(c, p, io);
+}
+int mbm_couple_mb_batch(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io *io) {
+  if (!c || c->inner_bc != MBM_BC_MB) return MBM_RC_BAD_ARG;
+  return mbm_couple_batch(c, p, io);
+}
+int mbm_stefan_xt_batch(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io *io) {
+  if (!c || c->inner_bc != MBM_BC_STEFAN || c->dt_mode != MBM_DT_STEFAN) return MBM_RC_BAD_ARG;
+  if (!p || !p->coeff_up || !p->coeff_do || !p->C_leftB || !p->C_rightB) return MBM_RC_BAD_ARG;
+  return mbm_couple_batch(c, p, io);
+}
+
+int mbm_simple_diff_batch(const mbm_common *c, const mbm_simple_params *p, mbm_simple_io *io) {
+  int rc = check_common(c);
+  if (rc) return rc;
+  if (!p || !io || !p->Di || !p->rho || !p->dx || !p->t_tot || !p->CFL || !p->BCout || !p->t_ar || !p->T_ar)
+    return MBM_RC_BAD_ARG;
+  if (!io->x || !io->C || !io->res || !io->t || !io->dt || !io->it || !io->status) return MBM_RC_BAD_ARG;
+  if (c->flags & (MBM_FLAG_SOLVER_FAITHFUL | MBM_FLAG_SUM_JULIA)) return MBM_RC_UNSUPPORTED;
+  return run_sharded(c, [&](int m0, int m1, int dev, double *ks) { return simple_shard(c, p, io, m0, m1, dev, ks); });
+}
+
+int mbm_create_grid(int32_t M, int32_t capL, int32_t capR, const double *Ri, const int64_t *res, const double *MRefin,
+                    double *x_left, double *x_right, double *dx1, double *dx2, double *newton_R, int32_t *status) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return MBM_RC_NO_DEVICE;
+  if (M <= 0) return 0;
+  if (!Ri || !res || !MRefin || !x_left || !x_right || !status) return MBM_RC_BAD_ARG;
+  Stage st;
+  CK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+  const size_t n = (size_t)M;
+  const double *dRi = st.in(Ri, 2 * n);
+  const long long *dres = (const long long *)st.in(res, 2 * n);
+  const double *dMR = st.in(MRefin, n);
+  double *dxl = st.outonly(x_left, n * capL), *dxr = st.outonly(x_right, n * capR);
+  double *d1 = dx1 ? st.outonly(dx1, n) : nullptr, *d2 = dx2 ? st.outonly(dx2, n) : nullptr;
+  double *dnR = newton_R ? st.outonly(newton_R, n) : nullptr;
+  int *dst = st.outonly(status, n);
+  double *work = (double *)st.scratch(n * (size_t)capR * sizeof(double));
+  int rc = st.rc;
+  if (!rc) {
+    mbm::mbm_create_grid_kernel<256><<<M, 256, 0, st.stream>>>(M, capL, capR, dRi, dres, dMR, dxl, dxr, d1, d2, dnR, dst, work);
+    if (cudaGetLastError() != cudaSuccess) rc = MBM_RC_CUDA;
+  }
+  if (!rc) rc = st.copy_back();
+  if (!rc && cudaStreamSynchronize(st.stream) != cudaSuccess) rc = MBM_RC_CUDA;
+  st.release();
+  cudaStreamSynchronize(st.stream);
+  cudaStreamDestroy(st.stream);
+  return rc;
+}
+
+int mbm_calc_mass_vol(int32_t M, int32_t ndim, int32_t capL, int32_t capR, const double *x_left, const double *x_right,
+                      const double *C_left, const double *C_right, const int64_t *res, const double *rho, double *Mass) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return MBM_RC_NO_DEVICE;
+  if (M <= 0) return 0;
+  if (!x_left || !x_right || !C_left || !C_right || !res || !rho || !Mass) return MBM_RC_BAD_ARG;
+  Stage st;
+  CK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+  const size_t n = (size_t)M;
+  const double *dxl = st.in(x_left, n * capL), *dxr = st.in(x_right, n * capR);
+  const double *dcl = st.in(C_left, n * capL), *dcr = st.in(C_right, n * capR);
+  const long long *dres = (const long long *)st.in(res, 2 * n);
+  const double *drho = st.in(rho, 2 * n);
+  double *dM = st.outonly(Mass, n);
+  int rc = st.rc;
+  if (!rc) {
+    mbm::mbm_calc_mass_kernel<<<(M + 63) / 64, 64, 0, st.stream>>>(M, ndim, capL, capR, dxl, dxr, dcl, dcr, dres, drho, dM);
+    if (cudaGetLastError() != cudaSuccess) rc = MBM_RC_CUDA;
+  }
+  if (!rc) rc = st.copy_back();
+  if (!rc && cudaStreamSynchronize(st.stream) != cudaSuccess) rc = MBM_RC_CUDA;
+  st.release();
+  cudaStreamSynchronize(st.stream);
+  cudaStreamDestroy(st.stream);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,1000 @@
+// mbm_kernels.cuh — the batched time-stepping kernel: one CTA per ensemble member, the member's
+// whole state resident in shared memory (or in a global workspace for very long profiles) across all
+// time steps of the call.  Loop body = reference main_codes/Diff_couple_1D_general_{MB,Flux}.jl:87-132,
+// Chemical_Stefan_problem_XT.jl:100-149, Simple_Diff_1D_general.jl:67-99.
+#pragma once
+#include "mbm_device.cuh"
+
+namespace mbm {
+
+enum { BC_NONE = 0, BC_FLUX = 1, BC_MB = 2, BC_STEFAN = 3, BC_HOLD = 4 };
+enum { DT_FIND = 0, DT_ADV = 1, DT_STEFAN = 2, DT_SIMPLE = 3 };
+enum { F_NEWTON_WARM = 1, F_RECORD = 2, F_MASS_FINAL = 0x80 };
+
+struct KArgs {
+  int M, ndim, hist_len, capL, capR, capS, inner_bc, dt_mode;
+  unsigned flags;
+  int use_global, pstride /*1 simple, 2 couple*/, pad_;
+  long long max_steps, rec_cap;
+  double *workspace;
+  // parameters
+  const double *Di, *D0, *Ea, *rho, *V_ip, *t_tot, *CFL, *MRefin, *s_dx;
+  const int *BCout;
+  const long long *resmin;
+  const double *t_ar, *T_ar, *KD_ar;
+  long long t_stride, T_stride, KD_stride;
+  double R;
+  const double *coeff_up, *coeff_do;
+  long long coeff_stride;
+  const double *C_leftB, *C_rightB;
+  int nd, pad2_;
+  const double *dens_X, *dens_T, *dens_left, *dens_right;
+  // state
+  double *x_left, *C_left, *x_right, *C_right;
+  long long *res;
+  double *Ri, *t, *dt;
+  long long *it;
+  double *dx1, *dx2, *Mass0, *Mass, *newton_R, *last;
+  int *status, *warn;
+  unsigned long long *idx_hash;
+  long long *node_steps;
+  double *rec;
+  double *s_D;  // simple: io.D
+};
+
+// per-member scalars, shared by the CTA
+struct Scal {
+  double t, dt, t_tot, CFL, MRefin, V, Ri1, Ri2, KD, T, D_l, D_r, rho1, rho2, Mass0, newton_R, dx1, dx2;
+  double Di0, Di1, D00, D01, Ea0, Ea1, R, sdx;
+  double a_if, b_if, Co_first, Co_last;
+  double KDmin, KDmax, Tmin, Tmax, tmin, tmax;
+  double cu0, cu1, cu2, cd0, cd1, cd2, CLB, CRB;
+  double grid_d, grid_S, grid_total;
+  double red[128];
+  long long it, steps, node_steps, resmin1, resmin2;
+  unsigned long long hash;
+  int n1, n2, gap, nr1, nr2, Fl, status, warn, bc0, bc1, hidx, arrhenius;
+  int m, KL, KR, nbL, nbR;
+};
+
+template <int T>
+__device__ __forceinline__ void cta_sync() {
+  if (T == 32) __syncwarp(); else __syncthreads();
+}
+
+// block-wide sum of up to 4 values; result broadcast to all threads. scratch: S->red (>= 4*T/32 doubles)
+template <int T>
+__device__ __forceinline__ void block_sum4(double v[4], double *scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = warp_sum(v[k]);
+  if (T == 32) return;
+  cta_sync<T>();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) scratch[w * 4 + k] = v[k];
+  }
+  cta_sync<T>();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double s = 0.0;
+    for (int ww = 0; ww < T / 32; ++ww) s += scratch[ww * 4 + k];
+    v[k] = s;
+  }
+}
+
+// ---- canonical scan (tiles of 8, Hillis-Steele over 32 tiles, sequential over groups) ---------------
+// Computes the inclusive scan of gen(i), i = 0..n-1, into out[0..n-1] (shared or global memory).
+// OP = 0: sum, 1: product.  gtot: scratch for group totals (>= ceil(n/256) doubles).  All threads call.
+template <int T, int OP, typename Gen>
+__device__ __forceinline__ void scan_canonical(Gen gen, int n, double *out, double *gtot) {
+  const double ident = OP ? 1.0 : 0.0;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = T / 32;
+  const int ngroups = (n + 255) >> 8;
+  for (int g = w; g < ngroups; g += W) {
+    const int base = (g * 32 + lane) * 8;
+    double loc[8];
+    double s = ident;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = base + k;
+      if (i < n) {
+        const double v = gen(i);
+        s = (k == 0) ? v : (OP ? xmul(s, v) : xadd(s, v));
+      }
+      loc[k] = s;
+    }
+    double inc = s;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const double o = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc = OP ? xmul(o, inc) : xadd(o, inc);
+    }
+    double Eq = __shfl_up_sync(0xffffffffu, inc, 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = base + k;
+      if (i < n) out[i] = (lane == 0) ? loc[k] : (OP ? xmul(Eq, loc[k]) : xadd(Eq, loc[k]));
+    }
+    if (lane == 31) gtot[g] = inc;
+  }
+  cta_sync<T>();
+  if (ngroups > 1) {
+    for (int g = 1 + w; g < ngroups; g += W) {
+      double Og = gtot[0];
+      for (int gg = 1; gg < g; ++gg) Og = OP ? xmul(Og, gtot[gg]) : xadd(Og, gtot[gg]);
+      const int base = (g * 32 + lane) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = base + k;
+        if (i < n) out[i] = OP ? xmul(Og, out[i]) : xadd(Og, out[i]);
+      }
+    }
+    cta_sync<T>();
+  }
+}
+
+// ---- history lookup: linear_interpolation_1D (functions.jl:565-585) with a monotone cursor ---------
+// first interval i with x[i] <= t <= x[i+1]; t never decreases between calls so the cursor only advances.
+__device__ inline int lin_interp_cursor(const double *x, const double *y, int n, double t, int *cur, double xmin,
+                                        double xmax, double *out) {
+  if (t < xmin || t > xmax) return 6;
+  int i = *cur;
+  while (i + 2 < n && t > x[i + 1]) ++i;
+  while (i > 0 && t <= x[i] && t >= x[i - 1]) --i;   // exact-knot case: first matching interval
+  *cur = i;
+  const double x0 = x[i], y0 = y[i], x1 = x[i + 1], y1 = y[i + 1];
+  const double iv = xinv(xsub(x1, x0));
+  const double N2 = xmul(xsub(t, x0), iv);
+  const double N1 = xsub(1.0, N2);
+  *out = xadd(xmul(N1, y0), xmul(N2, y1));
+  return 0;
+}
+
+struct MemberPtrs {
+  const double *t_ar, *T_ar, *KD_ar;
+};
+
+// update_t_dependent_param! (functions.jl:1350-1378) / _simple! (:1402-1423); thread 0 only
+__device__ inline int update_t_dependent(Scal &S, const KArgs &A, const MemberPtrs &P, bool simple) {
+  double KD = 0.0, T;
+  int rc;
+  int cur = S.hidx;
+  if (!simple) {
+    rc = lin_interp_cursor(P.t_ar, P.KD_ar, A.hist_len, S.t, &cur, S.tmin, S.tmax, &KD);
+    if (rc) return rc;
+  }
+  rc = lin_interp_cursor(P.t_ar, P.T_ar, A.hist_len, S.t, &cur, S.tmin, S.tmax, &T);
+  if (rc) return rc;
+  S.hidx = cur;
+  if (S.t == S.t_tot) {
+    T = P.T_ar[A.hist_len - 1];
+    if (!simple) KD = P.KD_ar[A.hist_len - 1];
+  } else {
+    if (!simple && (KD < S.KDmin - 1e-12 || KD > S.KDmax + 1e-12)) return 4;
+    if (T < S.Tmin - 1e-12 || T > S.Tmax + 1e-12) return 5;
+  }
+  if (S.arrhenius) {
+    S.D_l = xmul(S.D00, exp(xmul(-S.Ea0, xinv(xmul(S.R, T)))));
+    if (!simple) S.D_r = xmul(S.D01, exp(xmul(-S.Ea1, xinv(xmul(S.R, T)))));
+  } else {
+    S.D_l = S.Di0;
+    S.D_r = S.Di1;
+  }
+  S.KD = KD;
+  S.T = T;
+  return 0;
+}
+
+// interp2 (functionsStefan.jl:93-112), scalar query; thread 0 only
+__device__ inline int interp2(const double *X1d, const double *Y1d, const double *Z, int nd, double xi, double yi,
+                              double *zi) {
+  if (!(xi >= X1d[0] && xi <= X1d[nd - 1])) return 9;
+  if (!(yi >= Y1d[0] && yi <= Y1d[nd - 1])) return 9;
+  int ix = -1, iy = -1;
+  for (int i = 0; i < nd; ++i) { if (X1d[i] < xi) ix = i; if (Y1d[i] < yi) iy = i; }
+  if (ix < 0 || iy < 0 || ix + 1 >= nd || iy + 1 >= nd) return 9;
+  const double dx = X1d[ix + 1] - X1d[ix], dy = Y1d[iy + 1] - Y1d[iy];
+  const double idd = 1.0 / (dx * dy);
+  const double w11 = (X1d[ix + 1] - xi) * (Y1d[iy + 1] - yi) * idd, w12 = (X1d[ix + 1] - xi) * (yi - Y1d[iy]) * idd;
+  const double w21 = (xi - X1d[ix]) * (Y1d[iy + 1] - yi) * idd, w22 = (xi - X1d[ix]) * (yi - Y1d[iy]) * idd;
+  *zi = w11 * Z[ix + (size_t)iy * nd] + w12 * Z[ix + (size_t)(iy + 1) * nd] + w21 * Z[ix + 1 + (size_t)iy * nd] +
+        w22 * Z[ix + 1 + (size_t)(iy + 1) * nd];
+  return 0;
+}
+
+// ---- scalar phase of one step (thread 0): dt, time, parameters, interface advection, new node counts ---
+__device__ inline void step_scalars(Scal &S, const KArgs &A, const MemberPtrs &P, int mem, double *X, double *C) {
+  const int bc = A.inner_bc;
+  int rc = 0;
+  if (bc == BC_NONE) {
+    S.dt = xmul(xmul(S.CFL, xmul(S.sdx, S.sdx)), xinv(S.D_l));            // calculate_dt, functions.jl:166
+  } else if (bc == BC_STEFAN) {
+    // dt carried from the previous step
+  } else if (A.dt_mode == DT_ADV) {
+    S.dt = xmul(xdiv(fmin(S.dx1, S.dx2), S.V), S.CFL);                     // C1.jl:93
+  } else {                                                                // find_dt, functions.jl:465-490
+    const double mn = fmin(S.dx1, S.dx2), mxD = fmax(S.D_l, S.D_r);
+    double dtV = xmul(mn, xinv(fabs(S.V)));
+    const double dtD = xmul(xmul(xmul(mn, mn), xinv(mxD)), 50.0);
+    dtV = xmul(dtV, 0.99);
+    if (S.V == 0.0) S.dt = xmul(dtD, S.CFL);
+    else if (dtV < dtD) S.dt = xmul(dtV, S.CFL);
+    else S.dt = xmul(dtD, S.CFL);
+  }
+  // update_time!, functions.jl:1442-1450
+  S.t = xadd(S.t, S.dt);
+  S.it += 1;
+  if (S.t > S.t_tot) { S.dt = xsub(S.dt, xsub(S.t, S.t_tot)); S.t = S.t_tot; }
+  const int n1 = S.n1, n2 = S.n2;
+  const int rb = n1 + S.gap;  // storage index of x_right[1]
+  if (bc == BC_STEFAN) {
+    int cur = S.hidx;
+    rc = lin_interp_cursor(P.t_ar, P.T_ar, A.hist_len, S.t, &cur, S.tmin, S.tmax, &S.T);
+    S.hidx = cur;
+    if (rc) { S.status = rc; return; }
+    const double Tt = S.T;
+    const double CLe = S.cd0 + S.cd1 * Tt + S.cd2 * (Tt * Tt);             // composition, functionsStefan.jl:67-71
+    const double CR1 = S.cu0 + S.cu1 * Tt + S.cu2 * (Tt * Tt);
+    C[n1 - 1] = CLe;
+    C[rb] = CR1;
+    const double dC = CR1 - CLe;
+    if (A.nd > 0) {
+      double rL, rR;
+      rc = interp2(A.dens_X, A.dens_T, A.dens_left, A.nd, S.CLB, Tt, &rL);
+      if (!rc) rc = interp2(A.dens_X, A.dens_T, A.dens_right, A.nd, S.CRB, Tt, &rR);
+      if (rc) { S.status = rc; return; }
+      S.rho1 = rL * (1.0 / rL);
+      S.rho2 = rR * (1.0 / rL);
+    }
+    const double JL = -S.D_l * S.rho1 * (C[n1 - 1] - C[n1 - 2]) * (1.0 / S.dx1);   // CSP :111
+    const double JR = -S.D_r * S.rho2 * (C[rb + 1] - C[rb]) * (1.0 / S.dx2);       // :112
+    S.V = (JR - JL) * (1.0 / dC);                                                  // :113
+    const double Rl = CLe * (1.0 / (1.0 - CLe)), Rr = CR1 * (1.0 / (1.0 - CR1));
+    S.KD = Rl * (1.0 / Rr);
+  } else {
+    rc = update_t_dependent(S, A, P, bc == BC_NONE);
+    if (rc) { S.status = rc; return; }
+  }
+  // advect_interface_regrid!, functions.jl:29-64
+  S.Fl = 0;
+  if (bc != BC_NONE && bc != BC_HOLD) {
+    const double Rnew = xadd(S.Ri1, xmul(S.V, S.dt));
+    if (S.V > 0.0) {
+      if (n1 + 1 > A.capL) { S.status = 10; return; }
+      S.Ri1 = Rnew;
+      X[n1] = Rnew; C[n1] = C[n1 - 1];
+      if (Rnew > X[rb + 1]) { S.status = 1; return; }
+      X[rb] = Rnew;
+      S.n1 = n1 + 1; S.gap = 0; S.Fl = 1;
+    } else if (S.V < 0.0) {
+      if (n2 + 1 > A.capR) { S.status = 10; return; }
+      S.Ri1 = Rnew;
+      X[n1] = Rnew; C[n1] = C[rb];
+      S.n2 = n2 + 1; S.gap = 0;
+      if (Rnew < X[n1 - 2]) { S.status = 2; return; }
+      X[n1 - 1] = Rnew;
+      S.Fl = 1;
+    } else {
+      S.Ri1 = Rnew;
+    }
+  }
+  if (S.Fl) {                                                            // regrid!, functions.jl:873-889
+    long long nr1 = S.n1, nr2 = S.n2;
+    if (S.V > 0.0) nr1 = (long long)rint(xmul(xmul(S.Ri1, xinv(xsub(S.Ri2, S.Ri1))), (double)nr2));
+    else nr2 = (long long)rint(xmul(xmul(S.Ri2, xinv(xsub(S.Ri2, S.Ri1))), (double)nr1));
+    if (nr1 < S.resmin1) nr1 = S.resmin1;
+    if (nr2 < S.resmin2) nr2 = S.resmin2;
+    if (nr1 > A.capL || nr2 > A.capR || nr1 < 3 || nr2 < 3) { S.status = 10; return; }
+    if (!(S.MRefin >= 1.0)) { S.status = 12; return; }
+    S.nr1 = (int)nr1; S.nr2 = (int)nr2;
+  }
+  S.node_steps += S.n1 + S.n2;
+}
+
+// ---- pchip slope at node i of one phase (functions.jl:786-806; value code, contraction allowed) ------
+__device__ __forceinline__ double pchip_slope(const double *x, const double *y, int n, int i) {
+  if (i == 0) {
+    const double h1 = x[1] - x[0], h2 = x[2] - x[1];
+    const double m1 = (y[1] - y[0]) * (1.0 / h1), m2 = (y[2] - y[1]) * (1.0 / h2);
+    double d = fma(fma(2.0, h1, h2), m1, -(h1 * m2)) * (1.0 / (h1 + h2));
+    if (m1 * m2 < 0.0 || m1 == 0.0 || m2 == 0.0) d = 0.0;
+    return d;
+  } else if (i == n - 1) {
+    const double h1 = x[n - 1] - x[n - 2], h2 = x[n - 2] - x[n - 3];
+    const double m1 = (y[n - 1] - y[n - 2]) * (1.0 / h1), m2 = (y[n - 2] - y[n - 3]) * (1.0 / h2);
+    double d = fma(fma(2.0, h1, h2), m1, -(h1 * m2)) * (1.0 / (h1 + h2));
+    if (m1 * m2 < 0.0 || m1 == 0.0 || m2 == 0.0) d = 0.0;
+    return d;
+  }
+  const double ihm = 1.0 / (x[i] - x[i - 1]), ihp = 1.0 / (x[i + 1] - x[i]);
+  const double mm = (y[i] - y[i - 1]) * ihm, mp = (y[i + 1] - y[i]) * ihp;
+  const double wm = 2.0 * ihm, wp = 2.0 * ihp;
+  double d = (wm * mm + wp * mp) * (1.0 / (wm + wp));
+  if (mm * mp < 0.0 || mm == 0.0 || mp == 0.0) d = 0.0;
+  const double lim = 3.0 * fmin(fabs(mm), fabs(mp));
+  const double ad = fmin(fabs(d), lim);
+  return (d > 0.0) ? ad : ((d < 0.0) ? -ad : d);
+}
+
+// pchip evaluation of one new node (functions.jl:809-837); x,y,d: old phase arrays (n nodes)
+__device__ __forceinline__ double pchip_eval_one(const double *x, const double *y, const double *d, int n, double Xj,
+                                                 int *kout, int *branch) {
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (x[mid] < Xj) lo = mid + 1; else hi = mid; }
+  const int c = lo;
+  if (c < n && x[c] == Xj) { *kout = c; *branch = 0; return y[c]; }
+  if (c == n) { *kout = n - 1; *branch = 1; return y[n - 1]; }
+  if (c == 0) { *kout = 0; *branch = 2; return y[0]; }
+  const int k = c - 1;
+  *kout = k; *branch = 3;
+  const double x1 = x[k], x2 = x[k + 1], y1 = y[k], y2 = y[k + 1], d1 = d[k], d2 = d[k + 1];
+  const double s = Xj - x1, h = x2 - x1;
+  const double ih = 1.0 / h, ih2 = ih * ih, ih3 = ih2 * ih;
+  const double s2 = s * s, s3 = s2 * s, h3 = h * h * h, smh = s - h;
+  const double t1 = (3.0 * h * s2 - 2.0 * s3) * ih3 * y2;
+  const double t2 = (h3 - 3.0 * h * s2 + 2.0 * s3) * ih3 * y1;
+  const double t3 = (s2 * smh) * ih2 * d2;
+  const double t4 = (s * (smh * smh)) * ih2 * d1;
+  return t1 + t2 + t3 + t4;
+}
+
+// ---- reduced-system solve (levels 2 and 3): warp 0 solves the T-row tridiagonal system with two right-
+// hand sides held in shared memory (rs: sub, rd: diag, ru: sup, r0, r1); solution overwrites r0, r1.
+template <int T>
+__device__ __forceinline__ void reduced_solve(double *rs, double *rd, double *ru, double *r0, double *r1) {
+  constexpr int RPL = T / 32;
+  const int lane = threadIdx.x;  // caller guarantees threadIdx.x < 32
+  const int g0 = lane * RPL;
+  double A[RPL], G[RPL], R0[RPL], R1[RPL];
+  // pass 2 (backward over interior rows): first row in terms of the two separators
+  double bA = 0.0, bG = -1.0, bR0 = 0.0, bR1 = 0.0;
+  if (RPL > 1) {
+    int g = g0 + RPL - 2;
+    double inv = 1.0 / rd[g];
+    bA = rs[g] * inv; bG = ru[g] * inv; bR0 = r0[g] * inv; bR1 = r1[g] * inv;
+#pragma unroll
+    for (int k = RPL - 3; k >= 0; --k) {
+      g = g0 + k;
+      const double e = ru[g];
+      inv = 1.0 / (rd[g] - e * bA);
+      bA = rs[g] * inv;
+      bG = -e * bG * inv;
+      bR0 = (r0[g] - e * bR0) * inv;
+      bR1 = (r1[g] - e * bR1) * inv;
+    }
+  }
+  // pass 1 (forward): every row in terms of previous separator and next row
+  {
+    double inv = 1.0 / rd[g0];
+    A[0] = rs[g0] * inv; G[0] = ru[g0] * inv; R0[0] = r0[g0] * inv; R1[0] = r1[g0] * inv;
+#pragma unroll
+    for (int k = 1; k < RPL; ++k) {
+      const int g = g0 + k;
+      const double sb = rs[g];
+      inv = 1.0 / (rd[g] - sb * G[k - 1]);
+      A[k] = -sb * A[k - 1] * inv;
+      G[k] = ru[g] * inv;
+      R0[k] = (r0[g] - sb * R0[k - 1]) * inv;
+      R1[k] = (r1[g] - sb * R1[k - 1]) * inv;
+    }
+  }
+  // level-3 row of this lane (separator = last row of the lane's chunk), normalised to diag 1
+  const double nA = __shfl_down_sync(0xffffffffu, bA, 1), nG = __shfl_down_sync(0xffffffffu, bG, 1);
+  const double nR0 = __shfl_down_sync(0xffffffffu, bR0, 1), nR1 = __shfl_down_sync(0xffffffffu, bR1, 1);
+  double ps, pu, p0, p1;
+  {
+    const double Gl = (lane == 31) ? 0.0 : G[RPL - 1];
+    const double dg = 1.0 - Gl * nA;
+    const double inv = 1.0 / dg;
+    ps = A[RPL - 1] * inv;
+    pu = -Gl * nG * inv;
+    p0 = (R0[RPL - 1] - Gl * nR0) * inv;
+    p1 = (R1[RPL - 1] - Gl * nR1) * inv;
+    if (lane == 31) pu = 0.0;
+    if (lane == 0) ps = 0.0;
+  }
+  // parallel cyclic reduction over the 32 lanes (rows stay normalised)
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    double ls = __shfl_up_sync(0xffffffffu, ps, d), lu = __shfl_up_sync(0xffffffffu, pu, d);
+    double l0 = __shfl_up_sync(0xffffffffu, p0, d), l1 = __shfl_up_sync(0xffffffffu, p1, d);
+    double hs = __shfl_down_sync(0xffffffffu, ps, d), hu = __shfl_down_sync(0xffffffffu, pu, d);
+    double h0 = __shfl_down_sync(0xffffffffu, p0, d), h1 = __shfl_down_sync(0xffffffffu, p1, d);
+    if (lane < d) { ls = 0.0; lu = 0.0; l0 = 0.0; l1 = 0.0; }
+    if (lane + d > 31) { hs = 0.0; hu = 0.0; h0 = 0.0; h1 = 0.0; }
+    const double dg = 1.0 - ps * lu - pu * hs;
+    const double inv = 1.0 / dg;
+    const double n0 = (p0 - ps * l0 - pu * h0) * inv;
+    const double n1 = (p1 - ps * l1 - pu * h1) * inv;
+    const double ns = -ps * ls * inv;
+    const double nu = -pu * hu * inv;
+    ps = ns; pu = nu; p0 = n0; p1 = n1;
+  }
+  // p0,p1 = separator values of this lane; back-substitute inside the lane's chunk
+  double sp0 = __shfl_up_sync(0xffffffffu, p0, 1), sp1 = __shfl_up_sync(0xffffffffu, p1, 1);
+  if (lane == 0) { sp0 = 0.0; sp1 = 0.0; }
+  double c0 = p0, c1 = p1;
+  r0[g0 + RPL - 1] = c0; r1[g0 + RPL - 1] = c1;
+#pragma unroll
+  for (int k = RPL - 2; k >= 0; --k) {
+    c0 = R0[k] - A[k] * sp0 - G[k] * c0;
+    c1 = R1[k] - A[k] * sp1 - G[k] * c1;
+    r0[g0 + k] = c0; r1[g0 + k] = c1;
+  }
+}
+
+// ======================================================================================================
+// The kernel
+// ======================================================================================================
+template <int T>
+__global__ void __launch_bounds__(T) mbm_step_kernel(const KArgs A, const int member0) {
+  extern __shared__ double smem[];
+  __shared__ Scal S;
+  __shared__ double redS[T], redD[T], redU[T], red0[T], red1[T];   // reduced system
+  __shared__ double exA[T], exG[T], exR[T];                        // pass-2 results of every chunk
+
+  const int tid = threadIdx.x;
+  const int mem = member0 + blockIdx.x;
+  if (mem >= A.M) return;
+  const int capS = A.capS;
+  const size_t per_cta = 5 * (size_t)capS + (size_t)(capS / 256 + 8);
+  double *base = A.use_global ? (A.workspace + (size_t)blockIdx.x * per_cta) : smem;
+  double *gtot = base + 5 * (size_t)capS;                          // scan group totals
+  double *X = base, *C = base + capS, *Dd = base + 2 * (size_t)capS, *Xn = base + 3 * (size_t)capS,
+         *Cn = base + 4 * (size_t)capS;
+  const int bc = A.inner_bc;
+  const bool simple = (bc == BC_NONE);
+  MemberPtrs P;
+  P.t_ar = A.t_ar + (size_t)mem * A.t_stride;
+  P.T_ar = A.T_ar + (size_t)mem * A.T_stride;
+  P.KD_ar = A.KD_ar ? A.KD_ar + (size_t)mem * A.KD_stride : nullptr;
+
+  // ---------------- load member ----------------
+  if (tid == 0) {
+    const int ps = A.pstride;
+    S.status = A.status[mem];
+    S.warn = 0;
+    S.t = A.t[mem]; S.dt = A.dt[mem]; S.it = A.it[mem]; S.steps = 0;
+    S.t_tot = A.t_tot[mem]; S.CFL = A.CFL[mem];
+    S.Di0 = A.Di[(size_t)mem * ps]; S.Di1 = simple ? S.Di0 : A.Di[(size_t)mem * ps + 1];
+    S.D00 = A.D0 ? A.D0[(size_t)mem * ps] : 0.0; S.D01 = (A.D0 && !simple) ? A.D0[(size_t)mem * ps + 1] : 0.0;
+    S.Ea0 = A.Ea ? A.Ea[(size_t)mem * ps] : 0.0; S.Ea1 = (A.Ea && !simple) ? A.Ea[(size_t)mem * ps + 1] : 0.0;
+    S.R = A.R;
+    S.arrhenius = simple ? (S.Di0 == -1.0) : (S.Di0 == -1.0 && S.Di1 == -1.0);
+    S.bc0 = A.BCout[2 * (size_t)mem]; S.bc1 = A.BCout[2 * (size_t)mem + 1];
+    S.hash = A.idx_hash ? A.idx_hash[mem] : 0ull;
+    S.node_steps = A.node_steps ? A.node_steps[mem] : 0;
+    S.hidx = 0;
+    S.gap = 0; S.Fl = 0; S.V = 0.0; S.KD = 0.0; S.T = 0.0; S.D_l = 0.0; S.D_r = 0.0;
+    S.rho1 = 1.0; S.rho2 = 1.0; S.newton_R = 0.0; S.Mass0 = 0.0; S.Ri1 = 0.0; S.Ri2 = 0.0; S.MRefin = 1.0;
+    S.a_if = 0.0; S.b_if = 0.0;
+    if (simple) {
+      S.n1 = (int)A.res[mem]; S.n2 = 0;
+      S.sdx = A.s_dx[mem];
+      S.rho1 = A.rho[mem];
+      if (S.n1 < 3 || S.n1 > A.capL) { if (!S.status) S.status = 10; }
+    } else {
+      S.n1 = (int)A.res[2 * (size_t)mem]; S.n2 = (int)A.res[2 * (size_t)mem + 1];
+      S.gap = 1;
+      S.rho1 = A.rho[2 * (size_t)mem]; S.rho2 = A.rho[2 * (size_t)mem + 1];
+      S.V = A.V_ip ? A.V_ip[mem] : 0.0;
+      S.MRefin = A.MRefin[mem];
+      S.resmin1 = A.resmin[2 * (size_t)mem]; S.resmin2 = A.resmin[2 * (size_t)mem + 1];
+      S.Ri1 = A.Ri[2 * (size_t)mem]; S.Ri2 = A.Ri[2 * (size_t)mem + 1];
+      S.Mass0 = A.Mass0 ? A.Mass0[mem] : 0.0;
+      S.newton_R = A.newton_R ? A.newton_R[mem] : 0.0;
+      if (S.n1 < 3 || S.n2 < 3 || S.n1 > A.capL || S.n2 > A.capR) { if (!S.status) S.status = 10; }
+      if (bc == BC_STEFAN) {
+        const double *cu = A.coeff_up + (size_t)mem * A.coeff_stride, *cd = A.coeff_do + (size_t)mem * A.coeff_stride;
+        S.cu0 = cu[0]; S.cu1 = cu[1]; S.cu2 = cu[2]; S.cd0 = cd[0]; S.cd1 = cd[1]; S.cd2 = cd[2];
+        S.CLB = A.C_leftB[mem]; S.CRB = A.C_rightB[mem];
+      }
+    }
+    if (A.ndim < 1 || A.ndim > 3) { if (!S.status) S.status = 7; }
+  }
+  cta_sync<T>();
+  if (S.status != 0) return;   // frozen member: state untouched
+  {
+    const int n1 = S.n1, n2 = S.n2;
+    const double *gxl = A.x_left + (size_t)mem * A.capL, *gcl = A.C_left + (size_t)mem * A.capL;
+    for (int i = tid; i < n1; i += T) { X[i] = gxl[i]; C[i] = gcl[i]; }
+    if (!simple) {
+      const double *gxr = A.x_right + (size_t)mem * A.capR, *gcr = A.C_right + (size_t)mem * A.capR;
+      for (int i = tid; i < n2; i += T) { X[n1 + 1 + i] = gxr[i]; C[n1 + 1 + i] = gcr[i]; }
+    }
+    // min/max of the history arrays (range checks of update_t_dependent_param!, functions.jl:1360-1365)
+    double v[4] = {1e300, -1e300, 1e300, -1e300}, tm[2] = {1e300, -1e300};
+    for (int i = tid; i < A.hist_len; i += T) {
+      const double tt = P.t_ar[i], TT = P.T_ar[i];
+      tm[0] = fmin(tm[0], tt); tm[1] = fmax(tm[1], tt);
+      v[2] = fmin(v[2], TT); v[3] = fmax(v[3], TT);
+      if (P.KD_ar && bc != BC_STEFAN) { const double kd = P.KD_ar[i]; v[0] = fmin(v[0], kd); v[1] = fmax(v[1], kd); }
+    }
+    redS[tid] = v[0]; redD[tid] = v[1]; redU[tid] = v[2]; red0[tid] = v[3]; red1[tid] = tm[0]; exA[tid] = tm[1];
+    cta_sync<T>();
+    if (tid == 0) {
+      double a0 = 1e300, a1 = -1e300, a2 = 1e300, a3 = -1e300, a4 = 1e300, a5 = -1e300;
+      for (int k = 0; k < T; ++k) {
+        a0 = fmin(a0, redS[k]); a1 = fmax(a1, redD[k]); a2 = fmin(a2, redU[k]); a3 = fmax(a3, red0[k]);
+        a4 = fmin(a4, red1[k]); a5 = fmax(a5, exA[k]);
+      }
+      S.KDmin = a0; S.KDmax = a1; S.Tmin = a2; S.Tmax = a3; S.tmin = a4; S.tmax = a5;
+    }
+  }
+  cta_sync<T>();
+  if (tid == 0) {
+    const int n1 = S.n1;
+    if (!simple) {
+      S.dx1 = xsub(X[n1 - 1], X[n1 - 2]);                                  // create_grid!, functions.jl:366-367
+      S.dx2 = xsub(X[n1 + 2], X[n1 + 1]);
+    }
+    if (bc == BC_STEFAN) { S.D_l = S.Di0; S.D_r = S.Di1; S.T = P.T_ar[0]; }
+    else {
+      const int rc = update_t_dependent(S, A, P, simple);                  // pre-loop call (e.g. ..._MB.jl:75)
+      if (rc) S.status = rc;
+    }
+  }
+  cta_sync<T>();
+
+  const int ndim = A.ndim;
+  unsigned long long hash_local = 0ull;
+
+  // ======================================= time loop ===================================================
+  while (true) {
+    if (S.status != 0 || !(S.t < S.t_tot) || (A.max_steps > 0 && S.steps >= A.max_steps)) break;
+    cta_sync<T>();   // everyone has read the loop condition before thread 0 changes S
+    if (tid == 0) step_scalars(S, A, P, mem, X, C);
+    cta_sync<T>();
+    if (S.status != 0) break;
+
+    const int n1 = S.n1, n2 = S.n2, gap = S.gap, N = n1 + n2;
+    const double idt = 1.0 / S.dt;
+    const int p = n1 - 1;            // global row of the left interface node
+    const int q = n1;                // global row of the right interface node (couples only)
+    // -------- partition rows into chunks: block L = rows 0..nbL-1 (left->interface), block R = rows N-1..q+1
+    const int nbL = simple ? n1 : (n1 - 1), nbR = simple ? 0 : (n2 - 1);
+    int m = (nbL + nbR + T - 1) / T;
+    if (m < 1) m = 1;
+    int KL = (nbL + m - 1) / m, KR = (nbR + m - 1) / m;
+    while (KL + KR > T) { ++m; KL = (nbL + m - 1) / m; KR = (nbR + m - 1) / m; }
+    if (!(m & 1) && m > 1) {  // odd chunk length: conflict-free 8-byte shared-memory accesses
+      const int m2 = m + 1;
+      m = m2; KL = (nbL + m - 1) / m; KR = (nbR + m - 1) / m;
+    }
+    const bool active = tid < KL + KR;
+    const int blk = (tid < KL) ? 0 : 1;
+    const int jc = blk ? (tid - KL) : tid;               // chunk index inside the block
+    const int nb = blk ? nbR : nbL;
+    const int f = jc * m;                                 // first local row
+    const int l = min(f + m, nb) - 1;                     // last local row
+    const int dir = blk ? -1 : 1;
+    const int g0 = blk ? (N - 1) : 0;                     // global row of local row 0
+    const double Dph = blk ? S.D_r : S.D_l;
+    const bool has_beta = !simple;                        // block ends at an interface node
+    const bool dir0 = (blk ? (S.bc1 == 1) : (S.bc0 == 1));   // Dirichlet at local row 0
+    const bool dirLast = simple && (S.bc1 == 1);              // simple: Dirichlet at the last row
+#define SIDX(g) ((g) + (((g) >= n1) ? gap : 0))
+#define LOCS(ell) SIDX(g0 + dir * (ell))
+    // old boundary values (set_outer_bc! uses Co_l[1], Co_r[end]; Stefan/hold rows use C_left[end], C_right[1])
+    const double Co_first = C[0];
+    const double Co_last = C[SIDX(N - 1)];
+    const double a_old = simple ? 0.0 : C[SIDX(p)];
+    const double b_old = simple ? 0.0 : C[SIDX(q)];
+    double c_halo_prev = 0.0, c_halo_next = 0.0;
+    if (active) {
+      if (f > 0) c_halo_prev = C[LOCS(f - 1)];
+      if (l + 1 < nb || has_beta) c_halo_next = C[LOCS(l + 1)];
+    }
+    cta_sync<T>();
+
+    // ---------------- pass 2 (descending): assemble rows, store (diag,e,rhs), backward elimination ------
+    double subF = 0.0;   // coupling of row f to row f-1
+    double bA = 0.0, bG = -1.0, bR = 0.0;
+    if (active) {
+      // element between local ell and ell+1, seen from ell: Lself, Lnext, Lc (coupling), rhs parts
+      double x_next = 0.0, c_next = c_halo_next;
+      bool haveN = (l + 1 < nb) || has_beta;
+      if (haveN) x_next = X[LOCS(l + 1)];
+      double x_self = X[LOCS(l)], c_self = C[LOCS(l)];
+      double nAself = 0.0, nAnext = 0.0, nAc = 0.0, nkk = 0.0;   // element (ell, ell+1)
+      if (haveN) {
+        double A11, A12, A22, kk;
+        if (dir > 0) { elem_mats(x_self, x_next, Dph, idt, ndim, A11, A12, A22, kk); nAself = A11; nAnext = A22; }
+        else { elem_mats(x_next, x_self, Dph, idt, ndim, A11, A12, A22, kk); nAself = A22; nAnext = A11; }
+        nAc = A12; nkk = kk;
+      }
+      for (int ell = l; ell >= f; --ell) {
+        const int s = LOCS(ell);
+        double x_prev = 0.0, c_prev = 0.0;
+        const bool haveP = ell > 0;
+        double pAself = 0.0, pAnext = 0.0, pAc = 0.0, pkk = 0.0;   // element (ell-1, ell) seen from ell-1
+        if (haveP) {
+          x_prev = X[LOCS(ell - 1)];
+          c_prev = (ell == f) ? c_halo_prev : C[LOCS(ell - 1)];
+          double A11, A12, A22, kk;
+          if (dir > 0) { elem_mats(x_prev, x_self, Dph, idt, ndim, A11, A12, A22, kk); pAself = A11; pAnext = A22; }
+          else { elem_mats(x_self, x_prev, Dph, idt, ndim, A11, A12, A22, kk); pAself = A22; pAnext = A11; }
+          pAc = A12; pkk = kk;
+        }
+        double diag = (haveN ? (nAself - nkk) : 0.0) + (haveP ? (pAnext - pkk) : 0.0);
+        double rhs = (haveN ? (nAself * c_self + nAc * c_next) : 0.0) + (haveP ? (pAc * c_prev + pAnext * c_self) : 0.0);
+        const double e = haveN ? (nAc + nkk) : 0.0;       // coupling ell <-> ell+1 (FEM)
+        const double sub = haveP ? (pAc + pkk) : 0.0;     // coupling ell <-> ell-1 (FEM)
+        double sup = e, subrow = sub;
+        if (ell == 0 && dir0) { diag = 1.0; rhs = blk ? Co_last : Co_first; sup = 0.0; subrow = 0.0; }
+        if (dirLast && ell == nb - 1) { diag = 1.0; rhs = Co_last; sup = 0.0; subrow = 0.0; }
+        Dd[s] = diag; Xn[s] = e; C[s] = rhs;
+        if (ell == f) subF = subrow;
+        // backward elimination over interior rows (ell <= l-1)
+        if (ell == l - 1) {
+          const double inv = 1.0 / diag;
+          bA = subrow * inv; bG = sup * inv; bR = rhs * inv;
+        } else if (ell < l - 1) {
+          const double inv = 1.0 / (diag - sup * bA);
+          bA = subrow * inv;
+          bG = -sup * bG * inv;
+          bR = (rhs - sup * bR) * inv;
+        }
+        // slide
+        x_next = x_self; c_next = c_self; x_self = x_prev; c_self = c_prev;
+        nAself = pAself; nAnext = pAnext; nAc = pAc; nkk = pkk; haveN = true;
+      }
+    }
+    exA[tid] = bA; exG[tid] = bG; exR[tid] = bR;
+    cta_sync<T>();
+
+    // ---------------- pass 1 (ascending): normalised rows (A,G,R) + mass-balance functional --------------
+    double P0 = 0.0, Qa = 0.0, Qc = 0.0;   // sum_{rows of chunk} w*C = P0 + Qa*s_{j-1} + Qc*s_j
+    if (active) {
+      double Ap = 0.0, Gp = 0.0, Rp = 0.0, Qb = 0.0;
+      double Vm = 0.0, Vs = 0.0, Vp = 0.0;
+      const bool mb = (bc == BC_MB);
+      if (mb) {
+        const int gf = g0 + dir * f;
+        Vs = pow_ndim(X[SIDX(gf)], ndim);
+        Vm = (gf - dir >= 0 && gf - dir < N) ? pow_ndim(X[SIDX(gf - dir)], ndim) : Vs;
+      }
+      for (int ell = f; ell <= l; ++ell) {
+        const int s = LOCS(ell);
+        const double diag = Dd[s], e = Xn[s], rhs = C[s];
+        const double sub = (ell == f) ? subF : Xn[LOCS(ell - 1)];
+        double sup = e;
+        double subrow = sub;
+        if (ell == 0 && dir0) { sup = 0.0; subrow = 0.0; }
+        if (dirLast && ell == nb - 1) { sup = 0.0; subrow = 0.0; }
+        const double inv = 1.0 / (diag - subrow * Gp);
+        const double An = -subrow * Ap * inv + ((ell == f) ? subrow * inv : 0.0);
+        const double Gn = sup * inv;
+        const double Rn = (rhs - subrow * Rp) * inv;
+        if (ell > f) Xn[LOCS(ell - 1)] = Gp;   // previous row's e no longer needed: store its G
+        Dd[s] = An; C[s] = Rn;
+        if (mb) {
+          const int g = g0 + dir * ell;
+          Vp = pow_ndim(X[SIDX(g + dir)], ndim);   // next node exists (interface node at the block end)
+          // trapezoid weight in global order: 0.5*(V[g+1]-V[g]) + 0.5*(V[g]-V[g-1]); missing neighbour -> 0
+          const bool hasPrevNode = (g - dir >= 0 && g - dir < N);
+          const double w = dir > 0 ? (0.5 * (Vp - Vs) + (hasPrevNode ? 0.5 * (Vs - Vm) : 0.0))
+                                   : ((hasPrevNode ? 0.5 * (Vm - Vs) : 0.0) + 0.5 * (Vs - Vp));
+          if (ell < l) {
+            const double tq = Qb + w;
+            P0 = fma(tq, Rn, P0);
+            Qa = fma(-tq, An, Qa);
+            Qb = -tq * Gn;
+          } else {
+            Qc = Qb + w;
+          }
+          Vm = Vs; Vs = Vp;
+        }
+        Ap = An; Gp = Gn; Rp = Rn;
+      }
+      Xn[LOCS(l)] = Gp;
+      // reduced row of this chunk
+      const bool lastChunk = (jc == (blk ? KR : KL) - 1);
+      if (!lastChunk) {
+        const double nA = exA[tid + 1], nG = exG[tid + 1], nR = exR[tid + 1];
+        redS[tid] = Ap; redD[tid] = 1.0 - Gp * nA; redU[tid] = -Gp * nG; red0[tid] = Rp - Gp * nR; red1[tid] = 0.0;
+      } else {
+        redS[tid] = Ap; redD[tid] = 1.0; redU[tid] = 0.0; red0[tid] = Rp; red1[tid] = has_beta ? -Gp : 0.0;
+      }
+    } else {
+      redS[tid] = 0.0; redD[tid] = 1.0; redU[tid] = 0.0; red0[tid] = 0.0; red1[tid] = 0.0;
+    }
+    cta_sync<T>();
+    if (tid < 32) reduced_solve<T>(redS, redD, redU, red0, red1);
+    cta_sync<T>();
+
+    // ---------------- interface condition: 2x2 for (a,b) = (C[p], C[q]) ------------------------------------
+    double aif = 0.0, bif = 0.0;
+    if (!simple) {
+      if (bc == BC_FLUX) {
+        const double dxl = X[SIDX(p)] - X[SIDX(p - 1)], dxr = X[SIDX(q + 1)] - X[SIDX(q)];
+        const double al = -S.rho1 * S.D_l * (1.0 / dxl), be = S.V * S.rho1 + S.rho1 * S.D_l * (1.0 / dxl);
+        const double ga = -S.V * S.rho2 + S.rho2 * S.D_r * (1.0 / dxr), de = -S.rho2 * S.D_r * (1.0 / dxr);
+        const double U0 = red0[KL - 1], U1 = red1[KL - 1], W0 = red0[KL + KR - 1], W1 = red1[KL + KR - 1];
+        const double ca = be + al * U1, cb = ga + de * W1;
+        const double r = -(al * U0 + de * W0);
+        bif = r / (ca * S.KD + cb);
+        aif = S.KD * bif;
+      } else if (bc == BC_MB) {
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        if (active) {
+          const double s0 = red0[tid], s1 = red1[tid];
+          const double q0 = (jc > 0) ? red0[tid - 1] : 0.0, q1 = (jc > 0) ? red1[tid - 1] : 0.0;
+          const double c0 = P0 + Qa * q0 + Qc * s0, c1 = Qa * q1 + Qc * s1;
+          if (blk == 0) { v[0] = c0; v[1] = c1; } else { v[2] = c0; v[3] = c1; }
+        }
+        block_sum4<T>(v, S.red);
+        const double Vp_ = pow_ndim(X[SIDX(p)], ndim), Vq_ = pow_ndim(X[SIDX(q)], ndim);
+        const double wp = 0.5 * (Vq_ - Vp_) + 0.5 * (Vp_ - pow_ndim(X[SIDX(p - 1)], ndim));
+        const double wq = 0.5 * (pow_ndim(X[SIDX(q + 1)], ndim) - Vq_) + 0.5 * (Vq_ - Vp_);
+        bif = (S.Mass0 - (v[0] + v[2])) / ((v[1] + wp) * S.KD + (v[3] + wq));
+        aif = S.KD * bif;
+      } else {
+        aif = a_old; bif = b_old;
+      }
+    }
+    // ---------------- back-substitution ----------------------------------------------------------------
+    if (active) {
+      const double beta = blk ? bif : aif;
+      const double sj = red0[tid] + red1[tid] * beta;
+      const double sp = (jc > 0) ? (red0[tid - 1] + red1[tid - 1] * beta) : 0.0;
+      double cn = sj;
+      {
+        const int s = LOCS(l);
+        C[s] = cn;
+      }
+      for (int ell = l - 1; ell >= f; --ell) {
+        const int s = LOCS(ell);
+        cn = C[s] - Dd[s] * sp - Xn[s] * cn;
+        C[s] = cn;
+      }
+    }
+    if (!simple && tid == 0) { C[SIDX(p)] = aif; C[SIDX(q)] = bif; }
+    cta_sync<T>();
+
+    // ---------------- regrid!: new mesh + pchip (functions.jl:869-905) ----------------------------------
+    if (S.Fl) {
+      const int nr1 = S.nr1, nr2 = S.nr2;
+      const double Ri1 = S.Ri1, Ri2 = S.Ri2;
+      double *XLn = Xn, *XRn = Xn + nr1 + 1;   // new storage: left at [0,nr1), gap, right at [nr1+1, ...)
+      // slopes of the old profiles (both phases, incl. the inserted node)
+      const double *xl_o = X, *yl_o = C, *xr_o = X + n1 + gap, *yr_o = C + n1 + gap;
+      for (int i = tid; i < N; i += T) {
+        const int s = SIDX(i);
+        Dd[s] = (i < n1) ? pchip_slope(xl_o, yl_o, n1, i) : pchip_slope(xr_o, yr_o, n2, i - n1);
+      }
+      if (S.MRefin == 1.0) {                                               // functions.jl:396-400
+        for (int i = tid; i < nr1; i += T) XLn[i] = linrange_at(0.0, Ri1, nr1, i);
+        for (int i = tid; i < nr2; i += T) XRn[i] = linrange_at(Ri1, Ri2, nr2, i);
+        cta_sync<T>();
+      } else {
+        // left: dx_left = LinRange(1, 1/MRefin, nr1-1); x_left = [0; cumsum]*Ri1*inv(sum)   (:402-403)
+        const int nl = nr1 - 1;
+        const double bR = xmul(1.0, xinv(S.MRefin));
+        scan_canonical<T, 0>([&](int i) { return linrange_at(1.0, bR, nl, i); }, nl, XLn + 1, gtot);
+        const double total = XLn[nl];
+        const double isum = xinv(total);
+        cta_sync<T>();
+        for (int i = tid; i < nl; i += T) XLn[i + 1] = xmul(xmul(XLn[i + 1], Ri1), isum);
+        if (tid == 0) XLn[0] = xmul(xmul(0.0, Ri1), isum);
+        cta_sync<T>();
+        if (tid == 0) {                                                     // :406-408
+          const double Sg = xsub(Ri2, Ri1);
+          const double d = xsub(XLn[nr1 - 1], XLn[nr1 - 2]);
+          double x0 = 1.1;
+          if ((A.flags & F_NEWTON_WARM) && S.newton_R > 0.0) x0 = S.newton_R;
+          double Rt;
+          int wn = 0;
+          int rc = newton_solver(Sg, d, nr2 - 1, x0, &Rt, &wn);
+          if (rc && x0 != 1.1) { wn = 0; rc = newton_solver(Sg, d, nr2 - 1, 1.1, &Rt, &wn); }
+          if (rc) S.status = rc;
+          S.warn |= wn;
+          S.newton_R = Rt;
+          S.grid_d = d;
+        }
+        cta_sync<T>();
+        if (S.status != 0) break;
+        {                                                                   // :409-410
+          const double Rt = S.newton_R, d = S.grid_d;
+          const int n = nr2 - 1;
+          // dx_right by the canonical product scan of [d, R, R, ...]; staged in Cn, then cumsum into XRn+1
+          scan_canonical<T, 1>([&](int i) { return i == 0 ? d : Rt; }, n, Cn, gtot);
+          const double *dxr = Cn;
+          scan_canonical<T, 0>([&](int i) { return dxr[i]; }, n, XRn + 1, gtot);
+          for (int i = tid; i < n; i += T) XRn[i + 1] = xadd(Ri1, XRn[i + 1]);
+          if (tid == 0) XRn[0] = Ri1;
+          cta_sync<T>();
+        }
+      }
+      // pchip evaluation on the new meshes
+      const bool do_hash = (A.idx_hash != nullptr);
+      for (int j = tid; j < nr1 + nr2; j += T) {
+        const bool left = j < nr1;
+        const int jj = left ? j : (j - nr1);
+        const int sn = left ? j : (j + 1);
+        int k, br;
+        const double Pj = left ? pchip_eval_one(xl_o, yl_o, Dd, n1, Xn[sn], &k, &br)
+                               : pchip_eval_one(xr_o, yr_o, Dd + n1 + gap, n2, Xn[sn], &k, &br);
+        Cn[sn] = Pj;
+        if (do_hash) hash_local += idx_term(S.it, left ? 0 : 1, jj, k, br);
+      }
+      cta_sync<T>();
+      // swap buffers
+      { double *tp = X; X = Xn; Xn = tp; tp = C; C = Cn; Cn = tp; }
+      if (tid == 0) { S.n1 = nr1; S.n2 = nr2; S.gap = 1; }
+      cta_sync<T>();
+    }
+    // ---------------- end of step: dx1, dx2, Stefan dt, records ----------------------------------------
+    if (tid == 0) {
+      if (!simple) {
+        const int nn1 = S.n1, rb = S.n1 + S.gap;
+        S.dx1 = xsub(X[nn1 - 1], X[nn1 - 2]);
+        S.dx2 = xsub(X[rb + 1], X[rb]);
+        if (bc == BC_STEFAN) {                                              // CSP :147-149
+          const double mn = fmin(S.dx1, S.dx2), mxD = fmax(S.D_l, S.D_r);
+          const double dtV = mn * (1.0 / fabs(S.V));
+          const double dtD = (mn * mn) * (1.0 / mxD);
+          S.dt = fmin(dtD, dtV) * S.CFL;
+        }
+        const int nl_ = S.n1, rb2 = S.n1 + S.gap;
+        if (!isfinite(C[0]) || !isfinite(C[rb2 + S.n2 - 1]) || !isfinite(C[nl_ - 1]) || !isfinite(S.Ri1)) S.status = 11;
+      } else {
+        if (!isfinite(C[0]) || !isfinite(C[S.n1 - 1])) S.status = 11;
+      }
+      S.steps += 1;
+    }
+    if ((A.flags & F_RECORD) && A.rec) {
+      cta_sync<T>();
+      // calc_mass_vol (functions.jl:205-212) by a block reduction (order differs from the sequential cumsum)
+      const int nn1 = S.n1, nn2 = S.n2, rb = S.n1 + S.gap;
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int i = tid; i < nn1 - 1; i += T)
+        v[0] += 0.5 * (S.rho1 * pow_ndim(X[i + 1], ndim) - S.rho1 * pow_ndim(X[i], ndim)) * (C[i] + C[i + 1]);
+      for (int i = tid; i < nn2 - 1; i += T)
+        v[1] += 0.5 * (S.rho2 * pow_ndim(X[rb + i + 1], ndim) - S.rho2 * pow_ndim(X[rb + i], ndim)) * (C[rb + i] + C[rb + i + 1]);
+      block_sum4<T>(v, S.red);
+      if (tid == 0 && S.it >= 1 && S.it - 1 < A.rec_cap) {
+        double *r = A.rec + ((size_t)mem * (size_t)A.rec_cap + (size_t)(S.it - 1)) * 4;
+        r[0] = v[0] + v[1]; r[1] = S.T; r[2] = S.KD; r[3] = S.Ri1;
+      }
+    }
+    cta_sync<T>();
+  }
+#undef SIDX
+#undef LOCS
+  cta_sync<T>();
+  // ---------------- store member ----------------
+  {
+    const int n1 = S.n1, n2 = S.n2, rb = S.n1 + S.gap;
+    double *gxl = A.x_left + (size_t)mem * A.capL, *gcl = A.C_left + (size_t)mem * A.capL;
+    for (int i = tid; i < n1 && i < A.capL; i += T) { gxl[i] = X[i]; gcl[i] = C[i]; }
+    if (!simple) {
+      double *gxr = A.x_right + (size_t)mem * A.capR, *gcr = A.C_right + (size_t)mem * A.capR;
+      for (int i = tid; i < n2 && i < A.capR; i += T) { gxr[i] = X[rb + i]; gcr[i] = C[rb + i]; }
+    }
+    if ((A.flags & F_MASS_FINAL) && A.Mass) {
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int i = tid; i < n1 - 1; i += T)
+        v[0] += 0.5 * (S.rho1 * pow_ndim(X[i + 1], ndim) - S.rho1 * pow_ndim(X[i], ndim)) * (C[i] + C[i + 1]);
+      for (int i = tid; i < n2 - 1; i += T)
+        v[1] += 0.5 * (S.rho2 * pow_ndim(X[rb + i + 1], ndim) - S.rho2 * pow_ndim(X[rb + i], ndim)) * (C[rb + i] + C[rb + i + 1]);
+      block_sum4<T>(v, S.red);
+      if (tid == 0) A.Mass[mem] = v[0] + v[1];
+    }
+    if (A.idx_hash) {
+      // order-independent: sum of per-thread partial checksums
+      unsigned long long h = hash_local;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+      if ((tid & 31) == 0) atomicAdd(&S.hash, h);
+      cta_sync<T>();
+    }
+    if (tid == 0) {
+      A.status[mem] = S.status;
+      if (A.warn) A.warn[mem] = S.warn;
+      A.t[mem] = S.t; A.dt[mem] = S.dt; A.it[mem] = S.it;
+      if (simple) {
+        A.res[mem] = S.n1;
+        if (A.s_D) A.s_D[mem] = S.D_l;
+      } else {
+        A.res[2 * (size_t)mem] = S.n1; A.res[2 * (size_t)mem + 1] = S.n2;
+        A.Ri[2 * (size_t)mem] = S.Ri1; A.Ri[2 * (size_t)mem + 1] = S.Ri2;
+        if (A.dx1) A.dx1[mem] = S.dx1;
+        if (A.dx2) A.dx2[mem] = S.dx2;
+        if (A.newton_R) A.newton_R[mem] = S.newton_R;
+        if (A.last) {
+          double *L = A.last + 8 * (size_t)mem;
+          L[0] = S.D_l; L[1] = S.D_r; L[2] = S.KD; L[3] = S.T; L[4] = S.V; L[5] = S.rho1; L[6] = S.rho2; L[7] = (double)S.Fl;
+        }
+      }
+      if (A.idx_hash) A.idx_hash[mem] = S.hash;
+      if (A.node_steps) A.node_steps[mem] = S.node_steps;
+    }
+  }
+}
+
+// ---- pre-loop helpers on the device --------------------------------------------------------------------
+// create_grid! (functions.jl:364-370 -> define_new_grid :395-441): one CTA per member, meshes written to global.
+template <int T>
+__global__ void __launch_bounds__(T) mbm_create_grid_kernel(int M, int capL, int capR, const double *Ri,
+                                                            const long long *res, const double *MRefin, double *x_left,
+                                                            double *x_right, double *dx1, double *dx2, double *newton_R,
+                                                            int *status, double *work /* M*capR */) {
+  __shared__ double gtot[1024];
+  __shared__ double sh[4];
+  __shared__ int st;
+  const int mem = blockIdx.x, tid = threadIdx.x;
+  if (mem >= M) return;
+  const int nr1 = (int)res[2 * (size_t)mem], nr2 = (int)res[2 * (size_t)mem + 1];
+  double *XL = x_left + (size_t)mem * capL, *XR = x_right + (size_t)mem * capR, *W = work + (size_t)mem * capR;
+  const double Ri1 = Ri[2 * (size_t)mem], Ri2 = Ri[2 * (size_t)mem + 1], MR = MRefin[mem];
+  if (tid == 0) st = 0;
+  __syncthreads();
+  if (nr1 < 3 || nr2 < 3 || nr1 > capL || nr2 > capR) { if (tid == 0) status[mem] = 10; return; }
+  if (MR == 1.0) {
+    for (int i = tid; i < nr1; i += T) XL[i] = linrange_at(0.0, Ri1, nr1, i);
+    for (int i = tid; i < nr2; i += T) XR[i] = linrange_at(Ri1, Ri2, nr2, i);
+  } else if (!(MR > 1.0)) {
+    if (tid == 0) status[mem] = 12;
+    return;
+  } else {
+    const int nl = nr1 - 1;
+    const double bR = xmul(1.0, xinv(MR));
+    scan_canonical<T, 0>([&](int i) { return linrange_at(1.0, bR, nl, i); }, nl, XL + 1, gtot);
+    __syncthreads();
+    const double isum = xinv(XL[nl]);
+    __syncthreads();
+    for (int i = tid; i < nl; i += T) XL[i + 1] = xmul(xmul(XL[i + 1], Ri1), isum);
+    if (tid == 0) XL[0] = xmul(xmul(0.0, Ri1), isum);
+    __syncthreads();
+    if (tid == 0) {
+      const double Sg = xsub(Ri2, Ri1), d = xsub(XL[nr1 - 1], XL[nr1 - 2]);
+      double Rt; int wn = 0;
+      const int rc = newton_solver(Sg, d, nr2 - 1, 1.1, &Rt, &wn);
+      st = rc; sh[0] = Rt; sh[1] = d;
+    }
+    __syncthreads();
+    if (st) { if (tid == 0) status[mem] = st; return; }
+    const double Rt = sh[0], d = sh[1];
+    const int n = nr2 - 1;
+    scan_canonical<T, 1>([&](int i) { return i == 0 ? d : Rt; }, n, W, gtot);
+    __syncthreads();
+    scan_canonical<T, 0>([&](int i) { return W[i]; }, n, XR + 1, gtot);
+    __syncthreads();
+    for (int i = tid; i < n; i += T) XR[i + 1] = xadd(Ri1, XR[i + 1]);
+    if (tid == 0) { XR[0] = Ri1; if (newton_R) newton_R[mem] = Rt; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    status[mem] = 0;
+    if (dx1) dx1[mem] = xsub(XL[nr1 - 1], XL[nr1 - 2]);
+    if (dx2) dx2[mem] = xsub(XR[1], XR[0]);
+  }
+}
+
+// calc_mass_vol (functions.jl:205-212): sequential trapezoid cumsum exactly as the reference, one thread per member
+__global__ void mbm_calc_mass_kernel(int M, int ndim, int capL, int capR, const double *x_left, const double *x_right,
+                                     const double *C_left, const double *C_right, const long long *res,
+                                     const double *rho, double *Mass) {
+  const int mem = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mem >= M) return;
+  const int n1 = (int)res[2 * (size_t)mem], n2 = (int)res[2 * (size_t)mem + 1];
+  const double r1 = rho[2 * (size_t)mem], r2 = rho[2 * (size_t)mem + 1];
+  const double *xl = x_left + (size_t)mem * capL, *cl = C_left + (size_t)mem * capL;
+  const double *xr = x_right + (size_t)mem * capR, *cr = C_right + (size_t)mem * capR;
+  double Ml = 0.0, Mr = 0.0;
+  for (int i = 0; i + 1 < n1; ++i) {
+    const double dx = xsub(xmul(r1, pow_ndim(xl[i + 1], ndim)), xmul(r1, pow_ndim(xl[i], ndim)));
+    const double v = xmul(xmul(0.5, dx), xadd(cl[i], cl[i + 1]));
+    Ml = (i == 0) ? v : xadd(Ml, v);
+  }
+  for (int i = 0; i + 1 < n2; ++i) {
+    const double dx = xsub(xmul(r2, pow_ndim(xr[i + 1], ndim)), xmul(r2, pow_ndim(xr[i], ndim)));
+    const double v = xmul(xmul(0.5, dx), xadd(cr[i], cr[i + 1]));
+    Mr = (i == 0) ? v : xadd(Mr, v);
+  }
+  Mass[mem] = xadd(Ml, Mr);
+}
+
+}  // namespace mbm

@@ -1,0 +1,187 @@
+"""Parity tests proper: the CUDA path (through the C ABI of libmbm_b200.so) against the CPU oracle on
+identical inputs.  Bar: node counts, step counts, status codes and the regrid-index checksum bit-exact;
+profiles, meshes and interface position within 1e-10 relative (FP64), as BASELINE.json states."""
+import os
+
+import numpy as np
+import pytest
+
+from mbm_b200 import abi, drivers as d
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _relerr(a, b):
+    den = np.max(np.abs(a))
+    return 0.0 if den == 0 else float(np.max(np.abs(a - b)) / den)
+
+
+def compare(eo, eg, tol=TOL, ints=True, simple=False):
+    assert np.array_equal(eo.status, eg.status), (eo.status, eg.status)
+    if ints:
+        for k in ("res", "it", "node_steps") + (() if simple else ("idx_hash",)):
+            assert np.array_equal(eo.arrays[k], eg.arrays[k]), f"{k}: {eo.arrays[k]} vs {eg.arrays[k]}"
+    worst = 0.0
+    for m in range(eo.M):
+        if simple:
+            n = int(eo.res[m])
+            pairs = [(eo.C[m, :n], eg.C[m, :n])]
+        else:
+            pairs = list(zip(eo.member(m), eg.member(m)))
+        for a, b in pairs:
+            worst = max(worst, _relerr(a, b))
+    assert worst < tol, f"relative error {worst}"
+    if not simple:
+        assert _relerr(eo.Ri, eg.Ri) < 1e-13
+        assert _relerr(eo.t, eg.t) < 1e-13
+    return worst
+
+
+def run_both(pars_list, oracle, cuda_lib, max_steps, flags=0):
+    eo, _ = d.build_couple_ensemble(pars_list, oracle)
+    eg, _ = d.build_couple_ensemble(pars_list, cuda_lib)
+    assert np.array_equal(eo.x_left, eg.x_left) and np.array_equal(eo.x_right, eg.x_right), "create_grid differs"
+    assert _relerr(eo.Mass0, eg.Mass0) < 1e-15
+    assert eo.run(oracle, max_steps=max_steps, flags=flags | abi.FLAG_MASS_FINAL) == 0
+    assert eg.run(cuda_lib, max_steps=max_steps, flags=flags | abi.FLAG_MASS_FINAL) == 0
+    return eo, eg
+
+
+def test_library_identity(cuda_lib):
+    assert cuda_lib.mbm_backend() == b"cuda-sm_100a"
+    assert cuda_lib.mbm_device_count() >= 1
+
+
+@pytest.mark.parametrize("name,pars,steps", [
+    ("B1_flux_fixed", d.pars_B1, 400),
+    ("B2_flux_arrhenius", d.pars_B2, 400),
+    ("B4_flux_growth_sphere", d.pars_B4, 600),
+    ("B5_flux_growth_planar", d.pars_B5, 600),
+    ("C1_mb_growth_sphere", d.pars_C1, 600),
+    ("MBgrowth_mb_resorption_cyl", d.pars_MB_growth, 400),
+    ("MBmain_kd_t", d.pars_DCGMB, 0),
+    ("Fluxmain", d.pars_DCGF, 0),
+    ("DCNI_hold_dirichlet", d.pars_DCNI, 0),
+])
+def test_fixture_parity(oracle, cuda_lib, name, pars, steps):
+    """every shipped couple fixture of SURVEY.md §B, first `steps` steps (0 = whole run)"""
+    tol = 2e-9 if "arrhenius" in name else TOL   # CUDA exp vs glibc exp: 1-ulp D differences feed dt
+    eo, eg = run_both([pars()], oracle, cuda_lib, steps)
+    compare(eo, eg, tol=tol)
+    assert _relerr(eo.Mass, eg.Mass) < 1e-11
+
+
+def test_full_run_B5_known_answer(cuda_lib):
+    """reference test/test_B5.jl through the CUDA path: Smith (1955), rtol 1e-4"""
+    import benchmarks_ref as B
+    xl, xr, x0, Ri, Ri0, Cl, Cr, C0, C0r, KD0, n, maxC, Di, V, tt = d.B5(cuda_lib)
+    xan, Can = B.smith(xr, Cr, Ri, Di, tt, KD0, V, n)
+    ok, err = B.isapprox(Can, Cr, 1e-4)
+    assert ok, err
+
+
+def test_full_run_C1_known_answer(cuda_lib):
+    """reference test/test_C1.jl through the CUDA path: Rayleigh fractionation, rtol 1e-4"""
+    import benchmarks_ref as B
+    xl, xr, x0, Ri, Ri0, Cl, Cr, C0, C0r, n, maxC, KD0 = d.C1(cuda_lib)
+    Fs, Fl, Cliq, Cs, Clp, phi = B.rayleigh_fractionation(xl, Cl, Ri0, Ri, C0r, KD0, n)
+    iR, iM = B.trapezoidal_integration(Fs, Cs), B.trapezoidal_integration(phi**n, Clp)
+    assert abs(iR - iM) <= 1e-4 * max(abs(iR), abs(iM))
+
+
+def test_simple_A1(oracle, cuda_lib):
+    """examples/A1.jl whole run (842 steps) + the analytical gate of test/test_A1.jl"""
+    from mbm_b200.host import sinusoid_profile
+    import benchmarks_ref as B
+    eo = d.build_simple_ensemble([d.pars_A1()])
+    eg = eo.copy()
+    assert eo.run(oracle) == 0 and eg.run(cuda_lib) == 0
+    compare(eo, eg, simple=True)
+    p = d.pars_A1()
+    Can = sinusoid_profile(0.0, p["nmodes"], p["L"], p["Di"], eg.t[0], p["Amp"], eg.x[0, :500])
+    ok, err = B.isapprox(Can, eg.C[0, :500], 1e-4)
+    assert ok, err
+
+
+def test_simple_A2_prefix(oracle, cuda_lib):
+    """examples/A2.jl (sphere, Neumann/Dirichlet), first 2000 steps"""
+    eo = d.build_simple_ensemble([d.pars_A2()])
+    eg = eo.copy()
+    assert eo.run(oracle, max_steps=2000) == 0 and eg.run(cuda_lib, max_steps=2000) == 0
+    compare(eo, eg, simple=True)
+
+
+def test_stefan_main(oracle, cuda_lib):
+    """main_codes/Chemical_Stefan_problem_XT.jl (rho == 1), first 1500 steps: V comes from the solution, so
+    Ri and dt are value-level (1e-10), node counts and step counts must still agree exactly"""
+    eo = d.build_stefan_ensemble([d.pars_CSP()], oracle)
+    eg = d.build_stefan_ensemble([d.pars_CSP()], cuda_lib)
+    assert eo.run(oracle, max_steps=1500) == 0 and eg.run(cuda_lib, max_steps=1500) == 0
+    assert np.array_equal(eo.status, eg.status) and np.array_equal(eo.res, eg.res) and np.array_equal(eo.it, eg.it)
+    for a, b in zip(eo.member(0), eg.member(0)):
+        assert _relerr(a, b) < 1e-9
+    assert _relerr(eo.Ri, eg.Ri) < 1e-10
+
+
+def test_resume_equals_single_call(cuda_lib):
+    """state in/out: 3 calls of 100 steps == 1 call of 300 steps, bit for bit"""
+    ea, _ = d.build_couple_ensemble([d.pars_MB_growth()], cuda_lib)
+    eb = ea.copy()
+    assert ea.run(cuda_lib, max_steps=300) == 0
+    for _ in range(3):
+        assert eb.run(cuda_lib, max_steps=100) == 0
+    for k in ("x_left", "C_left", "x_right", "C_right", "res", "it", "Ri", "t", "idx_hash"):
+        assert np.array_equal(ea.arrays[k], eb.arrays[k]), k
+
+
+@pytest.mark.parametrize("threads", ["32", "64", "128", "256"])
+def test_thread_configs(oracle, cuda_lib, threads, monkeypatch):
+    """every CTA width gives the same integers and 1e-10 profiles (different chunking of the solve)"""
+    monkeypatch.setenv("MBM_THREADS", threads)
+    pars = []
+    for V, res in ((-1e-7, [60, 90]), (1e-7, [100, 150]), (-2e-7, [130, 131]), (3e-8, [33, 70])):
+        p = d.pars_MB_growth(); p.update(V_ip=V, res=res); pars.append(p)
+    eo, eg = run_both(pars, oracle, cuda_lib, 150)
+    compare(eo, eg)
+    pars = []
+    for V, res in ((1.0, [80, 120]), (0.5, [40, 64])):
+        p = d.pars_B4(); p.update(V_ip=V, res=res); pars.append(p)
+    eo, eg = run_both(pars, oracle, cuda_lib, 150)
+    compare(eo, eg)
+
+
+def test_error_status_codes(oracle, cuda_lib):
+    """per-member status mirrors the reference's throw sites; a failed member is frozen, others continue"""
+    good = d.pars_MB_growth(); good.update(res=[60, 90])
+    fast = d.pars_MB_growth(); fast.update(res=[60, 90], CFL=1.5)          # interface moves > 1 cell: functions.jl:50-53
+    eo, eg = run_both([good, fast, good], oracle, cuda_lib, 50)
+    assert list(eo.status) == list(eg.status)
+    assert eo.status[1] in (1, 2) and eo.status[0] == 0 and eo.status[2] == 0
+    for m in (0, 2):
+        for a, b in zip(eo.member(m), eg.member(m)):
+            assert _relerr(a, b) < TOL
+
+
+def test_capacity_status(oracle, cuda_lib):
+    p = d.pars_MB_growth(); p.update(res=[60, 90])
+    eo, _ = d.build_couple_ensemble([p], oracle, cap_left=64, cap_right=100)   # nr2 jumps to ~120 at step 1
+    eg, _ = d.build_couple_ensemble([p], cuda_lib, cap_left=64, cap_right=100)
+    assert eo.run(oracle, max_steps=5) == 0 and eg.run(cuda_lib, max_steps=5) == 0
+    assert eo.status[0] == 10 and eg.status[0] == 10
+
+
+def test_streaming_kernel_matches_resident(cuda_lib):
+    """the global-memory variant (MBM_FLAG_FORCE_STREAMING) runs the same arithmetic as the resident one"""
+    pars = []
+    for V in (-1e-7, 1e-7):
+        p = d.pars_MB_growth(); p.update(V_ip=V, res=[100, 150]); pars.append(p)
+    ea, _ = d.build_couple_ensemble(pars, cuda_lib)
+    eb = ea.copy()
+    assert ea.run(cuda_lib, max_steps=60) == 0
+    assert eb.run(cuda_lib, max_steps=60, flags=abi.FLAG_FORCE_STREAMING) == 0
+    for k in ("res", "it", "idx_hash"):
+        assert np.array_equal(ea.arrays[k], eb.arrays[k]), k
+    for m in range(2):
+        for a, b in zip(ea.member(m), eb.member(m)):
+            assert _relerr(a, b) < TOL
