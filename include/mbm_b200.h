@@ -232,6 +232,16 @@ int mbm_calc_mass_vol(int32_t n_members, int32_t ndim, int32_t cap_left, int32_t
 double mbm_last_kernel_seconds(void);
 int64_t mbm_last_kernel_launches(void);
 
+/* CUDA library only (oracle: no-ops returning 0).
+ * mbm_set_stream: launch the kernels of subsequent calls made by THIS host thread on the caller's
+ * cudaStream_t (e.g. torch's current stream) instead of a library-owned stream.  With
+ * MBM_FLAG_DEVICE_POINTERS the call then returns without synchronising, so the caller can bracket
+ * it with its own CUDA events.  NULL restores the default.
+ * mbm_measure_dfma_tflops: FP64 FMA micro-benchmark on `device` (the denominator of the FP64
+ * roofline; MEASURED_PEAKS.json has no FP64 entry).                                           */
+int mbm_set_stream(void *cuda_stream);
+double mbm_measure_dfma_tflops(int device);
+
 #ifdef __cplusplus
 }
 #endif

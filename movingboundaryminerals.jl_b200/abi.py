@@ -90,7 +90,7 @@ ABI_SYMBOLS = [
     "mbm_version", "mbm_device_count", "mbm_backend", "mbm_status_string",
     "mbm_simple_diff_batch", "mbm_couple_flux_batch", "mbm_couple_mb_batch",
     "mbm_stefan_xt_batch", "mbm_couple_batch", "mbm_create_grid", "mbm_calc_mass_vol",
-    "mbm_last_kernel_seconds", "mbm_last_kernel_launches",
+    "mbm_last_kernel_seconds", "mbm_last_kernel_launches", "mbm_set_stream", "mbm_measure_dfma_tflops",
 ]
 
 PKG_DIR = Path(__file__).resolve().parent
@@ -122,6 +122,10 @@ def bind(lib: C.CDLL) -> C.CDLL:
                                       _i64p, _dp, _dp]
     lib.mbm_last_kernel_seconds.restype = C.c_double
     lib.mbm_last_kernel_launches.restype = C.c_int64
+    lib.mbm_set_stream.restype = C.c_int
+    lib.mbm_set_stream.argtypes = [C.c_void_p]
+    lib.mbm_measure_dfma_tflops.restype = C.c_double
+    lib.mbm_measure_dfma_tflops.argtypes = [C.c_int]
     return lib
 
 

@@ -13,6 +13,8 @@
 
 namespace {
 
+thread_local cudaStream_t g_user_stream = nullptr;
+thread_local bool g_have_user_stream = false;
 thread_local double g_last_kernel_seconds = 0.0;
 thread_local long long g_last_kernel_launches = 0;
 double g_last_kernel_seconds_any = 0.0;
@@ -136,10 +138,13 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
     if (!A.workspace) return st->rc ? st->rc : MBM_RC_OOM;
   }
   A.use_global = use_global ? 1 : 0;
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
-  CK(cudaEventRecord(e0, s));
+  const bool async = g_have_user_stream && st->device_ptrs;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (!async) {
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, s));
+  }
   long long launches = 0;
   for (int off = 0; off < count; off += chunk) {
     const int n = (count - off < chunk) ? (count - off) : chunk;
@@ -154,6 +159,8 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
     if (rc) return rc;
     ++launches;
   }
+  g_last_kernel_launches = launches;
+  if (async) return 0;
   CK(cudaEventRecord(e1, s));
   CK(cudaStreamSynchronize(s));
   float ms = 0.f;
@@ -161,7 +168,6 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   if (kernel_seconds) *kernel_seconds = ms * 1e-3;
-  g_last_kernel_launches = launches;
   return 0;
 }
 
@@ -185,7 +191,9 @@ int couple_shard(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io 
   CK(cudaSetDevice(device));
   Stage st;
   st.device_ptrs = (c->flags & MBM_FLAG_DEVICE_POINTERS) != 0;
-  CK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+  const bool own_stream = !g_have_user_stream;
+  if (own_stream) CK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+  else st.stream = g_user_stream;
   const size_t n = (size_t)(m1 - m0), capL = c->cap_left, capR = c->cap_right, H = c->hist_len;
   mbm::KArgs A;
   memset(&A, 0, sizeof(A));
@@ -244,11 +252,12 @@ int couple_shard(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io 
     A.rec = st.inout(io->rec + 4 * (size_t)c->rec_cap * (size_t)m0, 4 * (size_t)c->rec_cap * n);
   int rc = st.rc;
   if (!rc) rc = launch_shard(A, 0, (int)n, device, c->flags, st.stream, &st, ksec);
+  const bool async = g_have_user_stream && st.device_ptrs;
   if (!rc) rc = st.copy_back();
-  if (!rc && cudaStreamSynchronize(st.stream) != cudaSuccess) rc = MBM_RC_CUDA;
+  if (!async && !rc && cudaStreamSynchronize(st.stream) != cudaSuccess) rc = MBM_RC_CUDA;
   st.release();
-  cudaStreamSynchronize(st.stream);
-  cudaStreamDestroy(st.stream);
+  if (!async) cudaStreamSynchronize(st.stream);
+  if (own_stream) cudaStreamDestroy(st.stream);
   return rc;
 }
 
@@ -257,7 +266,9 @@ int simple_shard(const mbm_common *c, const mbm_simple_params *p, mbm_simple_io 
   CK(cudaSetDevice(device));
   Stage st;
   st.device_ptrs = (c->flags & MBM_FLAG_DEVICE_POINTERS) != 0;
-  CK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+  const bool own_stream = !g_have_user_stream;
+  if (own_stream) CK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+  else st.stream = g_user_stream;
   const size_t n = (size_t)(m1 - m0), cap = c->cap_left, H = c->hist_len;
   mbm::KArgs A;
   memset(&A, 0, sizeof(A));
@@ -287,11 +298,12 @@ int simple_shard(const mbm_common *c, const mbm_simple_params *p, mbm_simple_io 
   A.node_steps = io->node_steps ? (long long *)st.inout(io->node_steps + m0, n) : nullptr;
   int rc = st.rc;
   if (!rc) rc = launch_shard(A, 0, (int)n, device, c->flags, st.stream, &st, ksec);
+  const bool async = g_have_user_stream && st.device_ptrs;
   if (!rc) rc = st.copy_back();
-  if (!rc && cudaStreamSynchronize(st.stream) != cudaSuccess) rc = MBM_RC_CUDA;
+  if (!async && !rc && cudaStreamSynchronize(st.stream) != cudaSuccess) rc = MBM_RC_CUDA;
   st.release();
-  cudaStreamSynchronize(st.stream);
-  cudaStreamDestroy(st.stream);
+  if (!async) cudaStreamSynchronize(st.stream);
+  if (own_stream) cudaStreamDestroy(st.stream);
   return rc;
 }
 
@@ -341,6 +353,55 @@ int mbm_device_count(void) {
 const char *mbm_backend(void) { return "cuda-sm_100a"; }
 
 double mbm_last_kernel_seconds(void) { return g_last_kernel_seconds_any; }
+
+int mbm_set_stream(void *cuda_stream) {
+  g_user_stream = (cudaStream_t)cuda_stream;
+  g_have_user_stream = (cuda_stream != nullptr);
+  return 0;
+}
+
+__global__ void mbm_dfma_kernel(double *out, int iters) {
+  double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+  double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+  const double b = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+double mbm_measure_dfma_tflops(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return 0.0;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(device);
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int blocks = sms * 8, threads = 256, iters = 20000;
+  double *out = nullptr;
+  if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) { cudaSetDevice(prev); return 0.0; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    mbm_dfma_kernel<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) * 1e-12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  cudaSetDevice(prev);
+  return best;
+}
 int64_t mbm_last_kernel_launches(void) { return g_last_kernel_launches_any; }
 
 const char *mbm_status_string(int32_t s) {

@@ -833,6 +833,8 @@ int mbm_device_count(void) { return 0; }
 const char *mbm_backend(void) { return "oracle-cpu"; }
 double mbm_last_kernel_seconds(void) { return 0.0; }
 int64_t mbm_last_kernel_launches(void) { return 0; }
+int mbm_set_stream(void *s) { (void)s; return 0; }
+double mbm_measure_dfma_tflops(int device) { (void)device; return 0.0; }
 
 const char *mbm_status_string(int32_t s) {
   switch (s) {

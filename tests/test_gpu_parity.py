@@ -154,7 +154,7 @@ def test_thread_configs(oracle, cuda_lib, threads, monkeypatch):
 def test_error_status_codes(oracle, cuda_lib):
     """per-member status mirrors the reference's throw sites; a failed member is frozen, others continue"""
     good = d.pars_MB_growth(); good.update(res=[60, 90])
-    fast = d.pars_MB_growth(); fast.update(res=[60, 90], CFL=1.5)          # interface moves > 1 cell: functions.jl:50-53
+    fast = d.pars_MB_growth(); fast.update(res=[60, 90], CFL=8.0, V_ip=-1e-4, t_tot=50.0)         # interface moves > 1 cell: functions.jl:50-53
     eo, eg = run_both([good, fast, good], oracle, cuda_lib, 50)
     assert list(eo.status) == list(eg.status)
     assert eo.status[1] in (1, 2) and eo.status[0] == 0 and eo.status[2] == 0
