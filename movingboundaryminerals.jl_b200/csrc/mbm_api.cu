@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "../../include/mbm_b200.h"
-#include "mbm_kernels.cuh"
+#include "mbm_kernel_v2.cuh"
 
 namespace {
 
@@ -110,6 +110,44 @@ int launch_T(const mbm::KArgs &A, int member0, int count, bool use_global, size_
   return (cudaGetLastError() == cudaSuccess) ? 0 : MBM_RC_CUDA;
 }
 
+constexpr int V2_MAXM = 15;
+
+template <int T>
+int launch_v2_T(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
+  auto kern = mbm::mbm_step_kernel_v2<T, V2_MAXM>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) return MBM_RC_CUDA;
+  kern<<<count, T, smem_bytes, s>>>(A, member0);
+  return (cudaGetLastError() == cudaSuccess) ? 0 : MBM_RC_CUDA;
+}
+
+// shared-memory capacities of the tuned kernel: as large as the caps allow within (a) two CTAs per SM,
+// (b) one scan tile per thread per phase (9*T elements), (c) at most V2_MAXM rows per thread in the solve
+void v2_plan(int capL, int capR, int smem_per_sm, int *T2, int *kL, int *kR) {
+  int kl = capL, kr = capR;
+  if (const char *e = getenv("MBM_KCAP")) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2) { kl = a < capL ? a : capL; kr = b < capR ? b : capR; } }
+  const int each_max = 9 * 256 + 1;
+  if (kl > each_max) kl = each_max;
+  if (kr > each_max) kr = each_max;
+  const int static_est = (int)sizeof(mbm::Scal) + 8 * 256 * 8 + 3 * 16 * 8 + 64;
+  const int per_cta = (smem_per_sm - 2 * 1024) / 2 - static_est;
+  int sum_max = per_cta / (3 * 8) - 1;
+  const int rows_max = (256 - 2) * V2_MAXM;
+  if (sum_max > rows_max) sum_max = rows_max;
+  if (kl + kr > sum_max) {
+    const double f = (double)sum_max / (double)(kl + kr);
+    kl = (int)(kl * f); kr = sum_max - kl;
+  }
+  int T = 256;
+  if (kl <= 9 * 64 + 1 && kr <= 9 * 64 + 1 && kl + kr <= (64 - 2) * V2_MAXM) T = 64;
+  else if (kl <= 9 * 128 + 1 && kr <= 9 * 128 + 1 && kl + kr <= (128 - 2) * V2_MAXM) T = 128;
+  if (const char *e = getenv("MBM_V2_THREADS")) {
+    const int t = atoi(e);
+    if ((t == 64 || t == 128 || t == 256) && kl <= 9 * t + 1 && kr <= 9 * t + 1 && kl + kr <= (t - 2) * V2_MAXM) T = t;
+  }
+  *T2 = T; *kL = kl; *kR = kr;
+}
+
 size_t static_smem_for(int T) { return sizeof(mbm::Scal) + 8 * (size_t)T * sizeof(double) + 256; }
 
 // run one shard [m0, m1) of an already device-resident KArgs
@@ -138,6 +176,25 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
     if (!A.workspace) return st->rc ? st->rc : MBM_RC_OOM;
   }
   A.use_global = use_global ? 1 : 0;
+  const bool couple_pv = (A.inner_bc == MBM_BC_FLUX || A.inner_bc == MBM_BC_MB);
+  bool use_v2 = couple_pv && !use_global && !getenv("MBM_NO_CHAIN") && !getenv("MBM_NO_V2");
+  int T2 = 256;
+  if (use_v2) {
+    int smem_sm = 0;
+    CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+    v2_plan(A.capL, A.capR, smem_sm, &T2, &A.kcapL, &A.kcapR);
+    if (A.kcapL < 4 || A.kcapR < 4) use_v2 = false;
+  }
+  if (couple_pv && !getenv("MBM_NO_CHAIN")) {
+    const int Tr = (use_v2 && T2 > T) ? T2 : T;
+    A.recs = (double *)st->scratch((size_t)chunk * (size_t)Tr * mbm::REC_N * sizeof(double));
+    if (!A.recs) return st->rc ? st->rc : MBM_RC_OOM;
+  }
+  if (use_v2) {
+    A.steps_done = (long long *)st->scratch((size_t)count * sizeof(long long));
+    if (!A.steps_done) return st->rc ? st->rc : MBM_RC_OOM;
+    CK(cudaMemsetAsync(A.steps_done, 0, (size_t)count * sizeof(long long), s));
+  }
   const bool async = g_have_user_stream && st->device_ptrs;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (!async) {
@@ -149,6 +206,20 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
   for (int off = 0; off < count; off += chunk) {
     const int n = (count - off < chunk) ? (count - off) : chunk;
     int rc;
+    if (use_v2) {
+      // tuned kernel first; the general kernel then only continues members handed over with status -1
+      const size_t dyn2 = 3 * (size_t)(A.kcapL + 1 + A.kcapR) * sizeof(double);
+      mbm::KArgs A2 = A;
+      A2.only_deferred = 0;
+      switch (T2) {
+        case 64: rc = launch_v2_T<64>(A2, m0 + off, n, dyn2, s); break;
+        case 128: rc = launch_v2_T<128>(A2, m0 + off, n, dyn2, s); break;
+        default: rc = launch_v2_T<256>(A2, m0 + off, n, dyn2, s); break;
+      }
+      if (rc) return rc;
+      ++launches;
+      A.only_deferred = 1;
+    }
     switch (T) {
       case 32: rc = launch_T<32>(A, m0 + off, n, use_global, dyn, s); break;
       case 64: rc = launch_T<64>(A, m0 + off, n, use_global, dyn, s); break;

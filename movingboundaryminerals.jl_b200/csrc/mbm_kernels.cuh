@@ -40,6 +40,23 @@ struct KArgs {
   long long *node_steps;
   double *rec;
   double *s_D;  // simple: io.D
+  double *recs; // run-ahead step records: gridDim * T * REC_N doubles (global, L2 resident)
+  long long *steps_done;  // [M] steps completed in this call by the tuned kernel (hand-over to the general kernel)
+  int kcapL, kcapR;       // shared-memory capacities of the tuned kernel
+  int only_deferred, pad3_;  // general kernel: process only members handed over with status -1
+};
+
+// Run-ahead scalar chain.  For prescribed-velocity couples the sequence of step
+// scalars (dt, t, KD, T, D, Ri, node counts, last left spacing d) does not depend on the solution, and
+// the mesh quantities it needs are closed-form in two scan totals (csA, csB) that only change when the
+// left node count changes.  Thread 0 runs the chain for up to T steps, then T threads solve the T
+// cold-start Newton problems of reference src/functions.jl:732-757 in parallel (bit-identical iterates).
+enum { REC_DT = 0, REC_T, REC_KD, REC_TEMP, REC_DL, REC_DR, REC_RI1, REC_D, REC_R, REC_NR1, REC_NR2, REC_STATUS,
+       REC_WARN, REC_IT, REC_N };
+struct Chain {
+  double t, dt, Ri1, dx1, dx2, D_l, D_r, xl_m2, xr_1, csA, csB;
+  long long it, steps;
+  int n1, n2, cs_nl, hidx, need_scan, scan_nl, done, status, count, pos;
 };
 
 // per-member scalars, shared by the CTA
@@ -55,6 +72,8 @@ struct Scal {
   unsigned long long hash;
   int n1, n2, gap, nr1, nr2, Fl, status, warn, bc0, bc1, hidx, arrhenius;
   int m, KL, KR, nbL, nbR;
+  int use_chain, rec_status;
+  Chain ch;
 };
 
 template <int T>
@@ -83,20 +102,23 @@ __device__ __forceinline__ void block_sum4(double v[4], double *scratch) {
   }
 }
 
-// ---- canonical scan (tiles of 8, Hillis-Steele over 32 tiles, sequential over groups) ---------------
+// ---- canonical scan (tiles of 9, Hillis-Steele over 32 tiles, sequential over groups) ---------------
 // Computes the inclusive scan of gen(i), i = 0..n-1, into out[0..n-1] (shared or global memory).
-// OP = 0: sum, 1: product.  gtot: scratch for group totals (>= ceil(n/256) doubles).  All threads call.
+// OP = 0: sum, 1: product.  gtot: scratch for group totals (>= ceil(n/288) doubles).  All threads call.
+// The tile length is odd so that lanes touching consecutive tiles hit distinct 8-byte banks.
+constexpr int CSO_TILE = 9;
+constexpr int CSO_GROUP_ELEMS = 32 * CSO_TILE;
 template <int T, int OP, typename Gen>
 __device__ __forceinline__ void scan_canonical(Gen gen, int n, double *out, double *gtot) {
   const double ident = OP ? 1.0 : 0.0;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = T / 32;
-  const int ngroups = (n + 255) >> 8;
+  const int ngroups = (n + CSO_GROUP_ELEMS - 1) / CSO_GROUP_ELEMS;
   for (int g = w; g < ngroups; g += W) {
-    const int base = (g * 32 + lane) * 8;
-    double loc[8];
+    const int base = (g * 32 + lane) * CSO_TILE;
+    double loc[CSO_TILE];
     double s = ident;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < CSO_TILE; ++k) {
       const int i = base + k;
       if (i < n) {
         const double v = gen(i);
@@ -112,7 +134,7 @@ __device__ __forceinline__ void scan_canonical(Gen gen, int n, double *out, doub
     }
     double Eq = __shfl_up_sync(0xffffffffu, inc, 1);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < CSO_TILE; ++k) {
       const int i = base + k;
       if (i < n) out[i] = (lane == 0) ? loc[k] : (OP ? xmul(Eq, loc[k]) : xadd(Eq, loc[k]));
     }
@@ -123,9 +145,9 @@ __device__ __forceinline__ void scan_canonical(Gen gen, int n, double *out, doub
     for (int g = 1 + w; g < ngroups; g += W) {
       double Og = gtot[0];
       for (int gg = 1; gg < g; ++gg) Og = OP ? xmul(Og, gtot[gg]) : xadd(Og, gtot[gg]);
-      const int base = (g * 32 + lane) * 8;
+      const int base = (g * 32 + lane) * CSO_TILE;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < CSO_TILE; ++k) {
         const int i = base + k;
         if (i < n) out[i] = OP ? xmul(Og, out[i]) : xadd(Og, out[i]);
       }
@@ -292,6 +314,108 @@ __device__ inline void step_scalars(Scal &S, const KArgs &A, const MemberPtrs &P
   S.node_steps += S.n1 + S.n2;
 }
 
+
+// history lookup for the chain: same arithmetic as update_t_dependent, explicit state
+__device__ inline int chain_update_params(const Scal &S, const KArgs &A, const MemberPtrs &P, double t, int *cur,
+                                          double *KD, double *Tt, double *D_l, double *D_r) {
+  int rc = lin_interp_cursor(P.t_ar, P.KD_ar, A.hist_len, t, cur, S.tmin, S.tmax, KD);
+  if (rc) return rc;
+  rc = lin_interp_cursor(P.t_ar, P.T_ar, A.hist_len, t, cur, S.tmin, S.tmax, Tt);
+  if (rc) return rc;
+  if (t == S.t_tot) {
+    *Tt = P.T_ar[A.hist_len - 1];
+    *KD = P.KD_ar[A.hist_len - 1];
+  } else {
+    if (*KD < S.KDmin - 1e-12 || *KD > S.KDmax + 1e-12) return 4;
+    if (*Tt < S.Tmin - 1e-12 || *Tt > S.Tmax + 1e-12) return 5;
+  }
+  if (S.arrhenius) {
+    *D_l = xmul(S.D00, exp(xmul(-S.Ea0, xinv(xmul(S.R, *Tt)))));
+    *D_r = xmul(S.D01, exp(xmul(-S.Ea1, xinv(xmul(S.R, *Tt)))));
+  } else {
+    *D_l = S.Di0;
+    *D_r = S.Di1;
+  }
+  return 0;
+}
+
+// thread 0: advance the scalar chain by up to `maxrec` steps, writing one record per step.
+// Same operations, in the same order, as step_scalars + the closed-form mesh scalars of define_new_grid.
+__device__ inline void chain_build(Scal &S, const KArgs &A, const MemberPtrs &P, double *recs, int maxrec, int capL,
+                                   int capR) {
+  Chain &c = S.ch;
+  c.count = 0; c.pos = 0;
+  const double V = S.V;
+  while (c.count < maxrec) {
+    if (c.status != 0 || !(c.t < S.t_tot) || (A.max_steps > 0 && c.steps >= A.max_steps)) { c.done = 1; break; }
+    // ---- dt (find_dt functions.jl:465-490 / C1.jl:93) and update_time! (:1442-1450)
+    double dt;
+    if (A.dt_mode == DT_ADV) dt = xmul(xdiv(fmin(c.dx1, c.dx2), V), S.CFL);
+    else {
+      const double mn = fmin(c.dx1, c.dx2), mxD = fmax(c.D_l, c.D_r);
+      double dtV = xmul(mn, xinv(fabs(V)));
+      const double dtD = xmul(xmul(xmul(mn, mn), xinv(mxD)), 50.0);
+      dtV = xmul(dtV, 0.99);
+      if (V == 0.0) dt = xmul(dtD, S.CFL);
+      else if (dtV < dtD) dt = xmul(dtV, S.CFL);
+      else dt = xmul(dtD, S.CFL);
+    }
+    double t = xadd(c.t, dt);
+    if (t > S.t_tot) { dt = xsub(dt, xsub(t, S.t_tot)); t = S.t_tot; }
+    double KD, Tt, D_l, D_r;
+    int cur = c.hidx;
+    int rc = chain_update_params(S, A, P, t, &cur, &KD, &Tt, &D_l, &D_r);
+    // ---- advect_interface_regrid! (functions.jl:29-64) on scalars
+    const double Rnew = xadd(c.Ri1, xmul(V, dt));
+    int n1s = c.n1, n2s = c.n2;
+    if (!rc) {
+      if (V > 0.0) {
+        if (c.n1 + 1 > capL) rc = 10;
+        else if (Rnew > c.xr_1) rc = 1;
+        n1s = c.n1 + 1;
+      } else {
+        if (c.n2 + 1 > capR) rc = 10;
+        else if (Rnew < c.xl_m2) rc = 2;
+        n2s = c.n2 + 1;
+      }
+    }
+    long long nr1 = n1s, nr2 = n2s;
+    if (!rc) {                                                              // regrid! :873-889
+      if (V > 0.0) nr1 = (long long)rint(xmul(xmul(Rnew, xinv(xsub(S.Ri2, Rnew))), (double)nr2));
+      else nr2 = (long long)rint(xmul(xmul(S.Ri2, xinv(xsub(S.Ri2, Rnew))), (double)nr1));
+      if (nr1 < S.resmin1) nr1 = S.resmin1;
+      if (nr2 < S.resmin2) nr2 = S.resmin2;
+      if (nr1 > capL || nr2 > capR || nr1 < 3 || nr2 < 3) rc = 10;
+    }
+    if (!rc && (int)nr1 - 1 != c.cs_nl) {      // left scan totals for this node count not cached: pause
+      c.need_scan = 1; c.scan_nl = (int)nr1 - 1;
+      break;
+    }
+    double *r = recs + (size_t)c.count * REC_N;
+    r[REC_DT] = dt; r[REC_T] = t; r[REC_KD] = KD; r[REC_TEMP] = Tt; r[REC_DL] = D_l; r[REC_DR] = D_r;
+    r[REC_RI1] = Rnew; r[REC_NR1] = (double)nr1; r[REC_NR2] = (double)nr2; r[REC_STATUS] = (double)rc;
+    r[REC_WARN] = 0.0; r[REC_IT] = (double)(c.it + 1); r[REC_D] = 0.0; r[REC_R] = 0.0;
+    c.count += 1;
+    c.steps += 1;
+    c.it += 1;
+    c.t = t; c.dt = dt; c.hidx = cur;
+    if (rc) { c.status = rc; c.done = 1; break; }
+    c.D_l = D_l; c.D_r = D_r;
+    c.Ri1 = Rnew;
+    // ---- closed-form mesh scalars of define_new_grid (:402-410) from the cached scan totals
+    const double isum = xinv(c.csA);
+    const double xl_last = xmul(xmul(c.csA, Rnew), isum);      // X_left[nr1-1]
+    const double xl_m2 = xmul(xmul(c.csB, Rnew), isum);        // X_left[nr1-2]
+    const double d = xsub(xl_last, xl_m2);
+    r[REC_D] = d;
+    c.xl_m2 = xl_m2;
+    c.xr_1 = xadd(Rnew, d);                                    // X_right[1] = Ri1 + dx_right[0]
+    c.dx1 = d;                                                 // regrid! :893
+    c.dx2 = xsub(c.xr_1, Rnew);                                // :894
+    c.n1 = (int)nr1; c.n2 = (int)nr2;
+  }
+}
+
 // ---- pchip slope at node i of one phase (functions.jl:786-806; value code, contraction allowed) ------
 __device__ __forceinline__ double pchip_slope(const double *x, const double *y, int n, int i) {
   if (i == 0) {
@@ -331,6 +455,56 @@ __device__ __forceinline__ double pchip_eval_one(const double *x, const double *
   const double x1 = x[k], x2 = x[k + 1], y1 = y[k], y2 = y[k + 1], d1 = d[k], d2 = d[k + 1];
   const double s = Xj - x1, h = x2 - x1;
   const double ih = 1.0 / h, ih2 = ih * ih, ih3 = ih2 * ih;
+  const double s2 = s * s, s3 = s2 * s, h3 = h * h * h, smh = s - h;
+  const double t1 = (3.0 * h * s2 - 2.0 * s3) * ih3 * y2;
+  const double t2 = (h3 - 3.0 * h * s2 + 2.0 * s3) * ih3 * y1;
+  const double t3 = (s2 * smh) * ih2 * d2;
+  const double t4 = (s * (smh * smh)) * ih2 * d1;
+  return t1 + t2 + t3 + t4;
+}
+
+
+// ---- value-code variants used by the tuned kernel (fast reciprocal, walking interval search) -----------
+__device__ __forceinline__ double frcp_(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+__device__ __forceinline__ double pchip_slope_fast(const double *x, const double *y, int n, int i) {
+  if (i == 0 || i == n - 1) return pchip_slope(x, y, n, i);
+  const double ihm = frcp_(x[i] - x[i - 1]), ihp = frcp_(x[i + 1] - x[i]);
+  const double mm = (y[i] - y[i - 1]) * ihm, mp = (y[i + 1] - y[i]) * ihp;
+  double d = (ihm * mm + ihp * mp) * frcp_(ihm + ihp);      // weights 2/h: the factor 2 cancels
+  if (mm * mp < 0.0 || mm == 0.0 || mp == 0.0) d = 0.0;
+  const double lim = 3.0 * fmin(fabs(mm), fabs(mp));
+  const double ad = fmin(fabs(d), lim);
+  return (d > 0.0) ? ad : ((d < 0.0) ? -ad : d);
+}
+// pchip evaluation with an interval search that walks from `guess` (count of old nodes below Xj);
+// identical branch/index semantics as pchip_eval_one (functions.jl:809-837)
+__device__ __forceinline__ double pchip_eval_walk(const double *x, const double *y, const double *d, int n, double Xj,
+                                                  int guess, int *cout, int *kout, int *branch) {
+  int c = min(max(guess, 0), n);
+  int steps = 0;
+  bool ok = true;
+  while (c < n && x[c] < Xj) { ++c; if (++steps > 16) { ok = false; break; } }
+  if (ok) while (c > 0 && !(x[c - 1] < Xj)) { --c; if (++steps > 16) { ok = false; break; } }
+  if (!ok) {
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (x[mid] < Xj) lo = mid + 1; else hi = mid; }
+    c = lo;
+  }
+  *cout = c;
+  if (c < n && x[c] == Xj) { *kout = c; *branch = 0; return y[c]; }
+  if (c == n) { *kout = n - 1; *branch = 1; return y[n - 1]; }
+  if (c == 0) { *kout = 0; *branch = 2; return y[0]; }
+  const int k = c - 1;
+  *kout = k; *branch = 3;
+  const double x1 = x[k], x2 = x[k + 1], y1 = y[k], y2 = y[k + 1], d1 = d[k], d2 = d[k + 1];
+  const double s = Xj - x1, h = x2 - x1;
+  const double ih = frcp_(h), ih2 = ih * ih, ih3 = ih2 * ih;
   const double s2 = s * s, s3 = s2 * s, h3 = h * h * h, smh = s - h;
   const double t1 = (3.0 * h * s2 - 2.0 * s3) * ih3 * y2;
   const double t2 = (h3 - 3.0 * h * s2 + 2.0 * s3) * ih3 * y1;
@@ -454,8 +628,12 @@ __global__ void __launch_bounds__(T) mbm_step_kernel(const KArgs A, const int me
   if (tid == 0) {
     const int ps = A.pstride;
     S.status = A.status[mem];
-    S.warn = 0;
+    S.warn = A.warn ? 0 : 0;
     S.t = A.t[mem]; S.dt = A.dt[mem]; S.it = A.it[mem]; S.steps = 0;
+    if (A.only_deferred) {
+      if (S.status == -1) { S.status = 0; S.steps = A.steps_done ? A.steps_done[mem] : 0; if (A.warn) S.warn = A.warn[mem]; }
+      else S.status = (S.status == 0) ? -2 : S.status;   // -2: nothing to do for this member
+    }
     S.t_tot = A.t_tot[mem]; S.CFL = A.CFL[mem];
     S.Di0 = A.Di[(size_t)mem * ps]; S.Di1 = simple ? S.Di0 : A.Di[(size_t)mem * ps + 1];
     S.D00 = A.D0 ? A.D0[(size_t)mem * ps] : 0.0; S.D01 = (A.D0 && !simple) ? A.D0[(size_t)mem * ps + 1] : 0.0;
@@ -537,16 +715,90 @@ __global__ void __launch_bounds__(T) mbm_step_kernel(const KArgs A, const int me
   }
   cta_sync<T>();
 
+  double *recs = A.recs ? (A.recs + (size_t)blockIdx.x * T * REC_N) : nullptr;
+  if (tid == 0) {
+    S.use_chain = (recs != nullptr) && (bc == BC_FLUX || bc == BC_MB) && (S.V != 0.0) && (S.MRefin > 1.0) &&
+                  (S.status == 0);
+    S.rec_status = 0;
+    if (S.use_chain) {
+      Chain &c = S.ch;
+      const int n1 = S.n1;
+      c.t = S.t; c.dt = S.dt; c.it = S.it; c.steps = S.steps; c.Ri1 = S.Ri1; c.dx1 = S.dx1; c.dx2 = S.dx2;
+      c.D_l = S.D_l; c.D_r = S.D_r; c.n1 = S.n1; c.n2 = S.n2; c.hidx = S.hidx;
+      c.xl_m2 = X[n1 - 2]; c.xr_1 = X[n1 + 2];
+      c.csA = 0.0; c.csB = 0.0; c.cs_nl = -1; c.need_scan = 0; c.scan_nl = 0; c.done = 0; c.status = 0;
+      c.count = 0; c.pos = 0;
+    }
+  }
+  cta_sync<T>();
   const int ndim = A.ndim;
   unsigned long long hash_local = 0ull;
 
   // ======================================= time loop ===================================================
+  int lpos = 0, lcount = 0;   // every thread tracks the batch cursor itself (no shared-memory race)
   while (true) {
-    if (S.status != 0 || !(S.t < S.t_tot) || (A.max_steps > 0 && S.steps >= A.max_steps)) break;
-    cta_sync<T>();   // everyone has read the loop condition before thread 0 changes S
-    if (tid == 0) step_scalars(S, A, P, mem, X, C);
-    cta_sync<T>();
-    if (S.status != 0) break;
+    if (S.use_chain) {
+      // ---------- run-ahead: refill the batch of step records when it is exhausted ----------
+      if (lpos >= lcount) {
+        if (S.ch.done) break;
+        cta_sync<T>();
+        if (S.ch.need_scan) {
+          // scan totals of dx_left = LinRange(1, 1/MRefin, nl) in the canonical order (Xn is free here)
+          const int nl = S.ch.scan_nl;
+          const double bR = xmul(1.0, xinv(S.MRefin));
+          scan_canonical<T, 0>([&](int i) { return linrange_at(1.0, bR, nl, i); }, nl, Xn, gtot);
+          if (tid == 0) { S.ch.csA = Xn[nl - 1]; S.ch.csB = Xn[nl - 2]; S.ch.cs_nl = nl; S.ch.need_scan = 0; }
+          cta_sync<T>();
+        }
+        if (tid == 0) chain_build(S, A, P, recs, T, A.capL, A.capR);
+        cta_sync<T>();
+        const int cnt = S.ch.count;
+        lcount = cnt; lpos = 0;
+        if (tid < cnt) {                      // one cold-start Newton per thread (functions.jl:732-757)
+          double *r = recs + (size_t)tid * REC_N;
+          if (r[REC_STATUS] == 0.0) {
+            double Rt; int wn = 0;
+            const int rc = newton_solver(xsub(S.Ri2, r[REC_RI1]), r[REC_D], (long long)r[REC_NR2] - 1, 1.1, &Rt, &wn);
+            r[REC_R] = Rt; r[REC_WARN] = (double)wn;
+            if (rc) r[REC_STATUS] = -(double)rc;   // negative: raised inside regrid!, after the solve
+          }
+        }
+        cta_sync<T>();
+        if (cnt == 0) { if (S.ch.done) break; continue; }
+      }
+      if (tid == 0) {
+        // consume one record: the scalar phase of this step
+        const double *r = recs + (size_t)lpos * REC_N;
+        S.dt = r[REC_DT]; S.t = r[REC_T]; S.KD = r[REC_KD]; S.T = r[REC_TEMP]; S.D_l = r[REC_DL]; S.D_r = r[REC_DR];
+        S.it = (long long)r[REC_IT];
+        const int st = (int)r[REC_STATUS];
+        S.rec_status = 0;
+        S.Fl = 0;
+        if (st > 0) { S.status = st; if (st == 1 || st == 2) S.Ri1 = r[REC_RI1]; }
+        else {
+          const int n1o = S.n1, n2o = S.n2, rb = S.n1 + S.gap;
+          const double Rnew = r[REC_RI1];
+          S.Ri1 = Rnew;
+          if (S.V > 0.0) { X[n1o] = Rnew; C[n1o] = C[n1o - 1]; X[rb] = Rnew; S.n1 = n1o + 1; }
+          else { X[n1o] = Rnew; C[n1o] = C[rb]; S.n2 = n2o + 1; X[n1o - 1] = Rnew; }
+          S.gap = 0; S.Fl = 1;
+          S.nr1 = (int)r[REC_NR1]; S.nr2 = (int)r[REC_NR2];
+          S.newton_R = r[REC_R]; S.grid_d = r[REC_D];
+          S.warn |= (int)r[REC_WARN];
+          if (st < 0) S.rec_status = -st;
+          S.node_steps += S.n1 + S.n2;
+        }
+      }
+      lpos += 1;
+      cta_sync<T>();
+      if (S.status != 0) break;
+    } else {
+      if (S.status != 0 || !(S.t < S.t_tot) || (A.max_steps > 0 && S.steps >= A.max_steps)) break;
+      cta_sync<T>();   // everyone has read the loop condition before thread 0 changes S
+      if (tid == 0) step_scalars(S, A, P, mem, X, C);
+      cta_sync<T>();
+      if (S.status != 0) break;
+    }
 
     const int n1 = S.n1, n2 = S.n2, gap = S.gap, N = n1 + n2;
     const double idt = 1.0 / S.dt;
@@ -779,7 +1031,9 @@ __global__ void __launch_bounds__(T) mbm_step_kernel(const KArgs A, const int me
         for (int i = tid; i < nl; i += T) XLn[i + 1] = xmul(xmul(XLn[i + 1], Ri1), isum);
         if (tid == 0) XLn[0] = xmul(xmul(0.0, Ri1), isum);
         cta_sync<T>();
-        if (tid == 0) {                                                     // :406-408
+        if (S.use_chain) {
+          if (tid == 0 && S.rec_status) S.status = S.rec_status;
+        } else if (tid == 0) {                                              // :406-408
           const double Sg = xsub(Ri2, Ri1);
           const double d = xsub(XLn[nr1 - 1], XLn[nr1 - 2]);
           double x0 = 1.1;

@@ -28,7 +28,7 @@
  *   - sum         -> pairwise + SIMD re-association (not reproducible; sequential here).
  *
  * Two orders of summation are provided for the grid generator:
- *   canonical (default): the order the CUDA kernels use (tiles of 8, Hillis-Steele over 32
+ *   canonical (default): the order the CUDA kernels use (tiles of 9, Hillis-Steele over 32
  *     tiles, sequential over groups) so that node counts, step counts and regrid indices are
  *     bit-identical between this oracle and the GPU; make_dx_right's sequential products use
  *     the same scan shape.
@@ -101,11 +101,11 @@ static inline double linrange_at(double a, double b, int64_t len, int64_t i) {
 /* ------------------------------------------------------------------------------------------ */
 /* Scans                                                                                       */
 /* ------------------------------------------------------------------------------------------ */
-#define CSO_TILE 8
+#define CSO_TILE 9
 #define CSO_GROUP 32
 
 /* canonical inclusive scan shared with the CUDA kernels (op: 0 = +, 1 = *).
- * out[i] = O_g (op) (E_q (op) s_k), where s_k is the sequential scan inside the tile of 8,
+ * out[i] = O_g (op) (E_q (op) s_k), where s_k is the sequential scan inside the tile of 9 (odd: bank-conflict-free on the GPU),
  * E_q the exclusive Hillis-Steele scan of the 32 tile totals of the group (identity for q = 0)
  * and O_g the sequential scan of the group totals (identity for g = 0).                       */
 static void scan_canonical(const double *v, int64_t n, double *out, int op) {

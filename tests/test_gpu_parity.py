@@ -185,3 +185,36 @@ def test_streaming_kernel_matches_resident(cuda_lib):
     for m in range(2):
         for a, b in zip(ea.member(m), eb.member(m)):
             assert _relerr(a, b) < TOL
+
+
+def test_handover_to_general_kernel(oracle, cuda_lib, monkeypatch):
+    """members that outgrow the tuned kernel's shared-memory capacity are handed over (status -1) to the general
+    kernel mid-call and finish there; the result is the same as the oracle's"""
+    monkeypatch.setenv("MBM_KCAP", "70,100")
+    pars = []
+    for V, res in ((-1e-7, [60, 90]), (1e-7, [60, 90]), (-1e-7, [40, 60]), (2e-7, [30, 40])):
+        p = d.pars_MB_growth(); p.update(V_ip=V, res=res); pars.append(p)
+    eo, eg = run_both(pars, oracle, cuda_lib, 120)
+    compare(eo, eg)
+
+
+def test_tuned_kernel_thread_configs(oracle, cuda_lib, monkeypatch):
+    """the tuned kernel at 64/128/256 threads per member"""
+    for t in ("64", "128", "256"):
+        monkeypatch.setenv("MBM_V2_THREADS", t)
+        pars = []
+        for V, res in ((-1e-7, [60, 90]), (1e-7, [100, 150]), (3e-8, [33, 70])):
+            p = d.pars_MB_growth(); p.update(V_ip=V, res=res); pars.append(p)
+        eo, eg = run_both(pars, oracle, cuda_lib, 100)
+        compare(eo, eg)
+
+
+def test_c4_shape_small_sample(oracle, cuda_lib):
+    """BASELINE.json configs[3] at full member size (n = 1024 per phase), 6 members x 30 steps"""
+    from mbm_b200 import ensembles as E
+    pars = E.c4_mb_growth_resorption(6, res=1024, max_steps=10_000)
+    eo, _ = d.build_couple_ensemble(pars, oracle, cap_left=2048, cap_right=2560)
+    eg, _ = d.build_couple_ensemble(pars, cuda_lib, cap_left=2048, cap_right=2560)
+    assert np.array_equal(eo.x_left, eg.x_left) and np.array_equal(eo.x_right, eg.x_right)
+    assert eo.run(oracle, max_steps=30) == 0 and eg.run(cuda_lib, max_steps=30) == 0
+    compare(eo, eg)
