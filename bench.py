@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--impl", default="mbm_b200", choices=["mbm_b200", "reference"])
     ap.add_argument("--members-per-gpu", type=int, default=int(os.environ.get("MBM_BENCH_MEMBERS", 8192)))
     ap.add_argument("--res", type=int, default=1024)
-    ap.add_argument("--tsteps", type=int, default=int(os.environ.get("MBM_BENCH_TSTEPS", 50)))
+    ap.add_argument("--tsteps", type=int, default=int(os.environ.get("MBM_BENCH_TSTEPS", 250)))
     ap.add_argument("--cpu-members", type=int, default=64)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -112,13 +112,21 @@ int launch_T(const mbm::KArgs &A, int member0, int count, bool use_global, size_
 
 constexpr int V2_MAXM = 15;
 
-template <int T>
-int launch_v2_T(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
-  auto kern = mbm::mbm_step_kernel_v2<T, V2_MAXM>;
+template <int T, int NDIM>
+int launch_v2_TN(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
+  auto kern = mbm::mbm_step_kernel_v2<T, V2_MAXM, NDIM>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return MBM_RC_CUDA;
   kern<<<count, T, smem_bytes, s>>>(A, member0);
   return (cudaGetLastError() == cudaSuccess) ? 0 : MBM_RC_CUDA;
+}
+template <int T>
+int launch_v2_T(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
+  switch (A.ndim) {
+    case 1: return launch_v2_TN<T, 1>(A, member0, count, smem_bytes, s);
+    case 2: return launch_v2_TN<T, 2>(A, member0, count, smem_bytes, s);
+    default: return launch_v2_TN<T, 3>(A, member0, count, smem_bytes, s);
+  }
 }
 
 // shared-memory capacities of the tuned kernel: as large as the caps allow within (a) two CTAs per SM,
@@ -177,7 +185,7 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
   }
   A.use_global = use_global ? 1 : 0;
   const bool couple_pv = (A.inner_bc == MBM_BC_FLUX || A.inner_bc == MBM_BC_MB);
-  bool use_v2 = couple_pv && !use_global && !getenv("MBM_NO_CHAIN") && !getenv("MBM_NO_V2");
+  bool use_v2 = couple_pv && !use_global && !getenv("MBM_NO_CHAIN") && !getenv("MBM_NO_V2") && A.ndim >= 1 && A.ndim <= 3;
   int T2 = 256;
   if (use_v2) {
     int smem_sm = 0;

@@ -21,7 +21,7 @@ __device__ __forceinline__ double xinv(double a) { return __ddiv_rn(1.0, a); }
 __device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
 
 // Base.Math.pow_body(x::Float64, n::Integer) (Julia 1.10 base/math.jl), as in oracle jl_pow_int
-__device__ __forceinline__ double jl_pow_int(double x, long long n) {
+__device__ __noinline__ double jl_pow_int(double x, long long n) {
   if (n == 0) return 1.0;
   double y = 1.0, xnlo = 0.0, ynlo = 0.0;
   if (n == 3) return xmul(xmul(x, x), x);
@@ -59,14 +59,14 @@ __device__ __forceinline__ double pow_ndim(double x, int ndim) {
 }
 
 // LinRange(a,b,len)[i], 0-based (Base.lerpi)
-__device__ __forceinline__ double linrange_at(double a, double b, long long len, long long i) {
+__device__ __noinline__ double linrange_at(double a, double b, long long len, long long i) {
   long long d = (len - 1 > 1) ? (len - 1) : 1;
   double t = xdiv((double)i, (double)d);
   return xadd(xmul(xsub(1.0, t), a), xmul(t, b));
 }
 
 // newton_solver, reference src/functions.jl:732-757 (operation for operation as the oracle)
-__device__ inline int newton_solver(double S, double d, long long n, double x0, double *root, int *warn) {
+__device__ __noinline__ int newton_solver(double S, double d, long long n, double x0, double *root, int *warn) {
   double x = x0, Res = 1e23;
   const double Sd = xmul(S, xinv(d));
   for (int i = 1; i <= 200; ++i) {

@@ -16,18 +16,26 @@ namespace mbm {
 __device__ __forceinline__ double frcp(double x) { return frcp_(x); }
 
 // element matrices with the fast reciprocal (reference src/functions.jl:525-540)
-__device__ __forceinline__ void elem_mats_fast(double x1, double x2, double D, double idt, int ndim, double &A11,
+template <int NDIM>
+__device__ __forceinline__ double powd(double x) {
+  if (NDIM == 1) return x;
+  if (NDIM == 2) return x * x;
+  return x * x * x;
+}
+
+template <int NDIM>
+__device__ __forceinline__ void elem_mats_fast(double x1, double x2, double D, double idt, double &A11,
                                                double &A12, double &A22, double &kk) {
   const double df = x1 - x2;
   const double idf = frcp(df);
-  if (ndim == 3) {
+  if (NDIM == 3) {
     const double x1s = x1 * x1, x2s = x2 * x2, x12 = x1 * x2;
     const double c30 = -df * (idt * (1.0 / 30.0)), c60 = -df * (idt * (1.0 / 60.0));
     A11 = (6.0 * x1s + 3.0 * x12 + x2s) * c30;
     A12 = (3.0 * x1s + 4.0 * x12 + 3.0 * x2s) * c60;
     A22 = (x1s + 3.0 * x12 + 6.0 * x2s) * c30;
     kk = (D * (1.0 / 3.0)) * (x1s + x12 + x2s) * idf;
-  } else if (ndim == 2) {
+  } else if (NDIM == 2) {
     const double c12 = -df * (idt * (1.0 / 12.0));
     A11 = (3.0 * x1 + x2) * c12;
     A12 = (x1 + x2) * c12;          // (x2^2 - x1^2)/12 = -(x1-x2)(x1+x2)/12
@@ -41,7 +49,7 @@ __device__ __forceinline__ void elem_mats_fast(double x1, double x2, double D, d
   }
 }
 
-template <int T, int MAXM>
+template <int T, int MAXM, int NDIM>
 __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const int member0) {
   extern __shared__ double smem[];
   __shared__ Scal S;
@@ -57,7 +65,7 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
   const int RB0 = kcapL + 1;                 // storage index of x_right[1] after a regrid
   double *X = smem, *C = smem + SZ, *W = smem + 2 * (size_t)SZ;
   const int bc = A.inner_bc;
-  const int ndim = A.ndim;
+  constexpr int ndim = NDIM;
   MemberPtrs P;
   P.t_ar = A.t_ar + (size_t)mem * A.t_stride;
   P.T_ar = A.T_ar + (size_t)mem * A.T_stride;
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
     S.Ri1 = A.Ri[2 * (size_t)mem]; S.Ri2 = A.Ri[2 * (size_t)mem + 1];
     S.Mass0 = A.Mass0 ? A.Mass0[mem] : 0.0;
     S.newton_R = A.newton_R ? A.newton_R[mem] : 0.0;
-    S.rec_status = 0;
+    S.rec_status = 0; S.nbL = -1; S.nbR = -1; S.m = 1; S.KL = 0; S.KR = 0;
     // eligibility: anything this kernel does not cover is handed to the general kernel (status -1)
     S.use_chain = 1;
     if (S.status == 0) {
@@ -194,6 +202,14 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
         S.warn |= (int)r[REC_WARN];
         if (st < 0) S.rec_status = -st;
         S.node_steps += S.n1 + S.n2;
+        if (S.n1 != S.nbL + 1 || S.n2 != S.nbR + 1) {   // rows per thread (odd: conflict-free), chunks per block
+          const int nbL = S.n1 - 1, nbR = S.n2 - 1;
+          int m = (nbL + nbR + T - 1) / T;
+          int KL = (nbL + m - 1) / m, KR = (nbR + m - 1) / m;
+          while (KL + KR > T) { ++m; KL = (nbL + m - 1) / m; KR = (nbR + m - 1) / m; }
+          if (!(m & 1)) { m += 1; KL = (nbL + m - 1) / m; KR = (nbR + m - 1) / m; }
+          S.m = m; S.KL = KL; S.KR = KR; S.nbL = nbL; S.nbR = nbR;   // m <= MAXM: host guarantees kcapL+kcapR <= (T-2)*MAXM
+        }
       }
     }
     lpos += 1;
@@ -204,11 +220,7 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
     const int n1 = S.n1, n2 = S.n2, rb = S.gap;
     const double idt = frcp(S.dt);
     const int nbL = n1 - 1, nbR = n2 - 1;
-    int m = (nbL + nbR + T - 1) / T;
-    int KL = (nbL + m - 1) / m, KR = (nbR + m - 1) / m;
-    while (KL + KR > T) { ++m; KL = (nbL + m - 1) / m; KR = (nbR + m - 1) / m; }
-    if (!(m & 1)) { m += 1; KL = (nbL + m - 1) / m; KR = (nbR + m - 1) / m; }
-    // (m <= MAXM is guaranteed by the host: kcapL + kcapR <= (T-2)*MAXM)
+    const int m = S.m, KL = S.KL, KR = S.KR;     // partition computed by thread 0 when the record was consumed
     const bool active = tid < KL + KR;
     const int blk = (tid < KL) ? 0 : 1;
     const int jc = blk ? (tid - KL) : tid;
@@ -241,20 +253,20 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
       if (haveP) {
         x_prev = X[ST(f - 1)];
         double A11, A12, A22, kk;
-        if (sdir > 0) { elem_mats_fast(x_prev, x_self, Dph, idt, ndim, A11, A12, A22, kk); pAnext = A22; }
-        else { elem_mats_fast(x_self, x_prev, Dph, idt, ndim, A11, A12, A22, kk); pAnext = A11; }
+        if (sdir > 0) { elem_mats_fast<NDIM>(x_prev, x_self, Dph, idt, A11, A12, A22, kk); pAnext = A22; }
+        else { elem_mats_fast<NDIM>(x_self, x_prev, Dph, idt, A11, A12, A22, kk); pAnext = A11; }
         pAc = A12; pkk = kk;
       }
       double Qb = 0.0, Vm = 0.0, Vs = 0.0;
-      if (mb) { Vs = pow_ndim(x_self, ndim); Vm = haveP ? pow_ndim(x_prev, ndim) : Vs; }
+      if (mb) { Vs = powd<NDIM>(x_self); Vm = haveP ? powd<NDIM>(x_prev) : Vs; }
       for (int k = 0; k < len; ++k) {
         const int ell = f + k;
         const int s = ST(ell);
         const double x_next = X[ST(ell + 1)];
         const double c_next = (k == len - 1) ? c_halo_next : C[ST(ell + 1)];
         double A11, A12, A22, kk, nAself, nAnext;
-        if (sdir > 0) { elem_mats_fast(x_self, x_next, Dph, idt, ndim, A11, A12, A22, kk); nAself = A11; nAnext = A22; }
-        else { elem_mats_fast(x_next, x_self, Dph, idt, ndim, A11, A12, A22, kk); nAself = A22; nAnext = A11; }
+        if (sdir > 0) { elem_mats_fast<NDIM>(x_self, x_next, Dph, idt, A11, A12, A22, kk); nAself = A11; nAnext = A22; }
+        else { elem_mats_fast<NDIM>(x_next, x_self, Dph, idt, A11, A12, A22, kk); nAself = A22; nAnext = A11; }
         double diag = (nAself - kk) + (haveP ? (pAnext - pkk) : 0.0);
         double rhs = (nAself * c_self + A12 * c_next) + (haveP ? (pAc * c_prev + pAnext * c_self) : 0.0);
         double sup = A12 + kk;
@@ -268,7 +280,7 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
         for (int kk2 = 0; kk2 < MAXM; ++kk2) if (kk2 == k) Areg[kk2] = An;
         W[s] = Gn; C[s] = Rn;
         if (mb) {
-          const double Vn = pow_ndim(x_next, ndim);
+          const double Vn = powd<NDIM>(x_next);
           // trapezoid weight 0.5*(V[g+1]-V[g]) + 0.5*(V[g]-V[g-1]) in global order (functions.jl:291-296)
           const double w = (sdir > 0) ? (0.5 * (Vn - Vs) + (haveP ? 0.5 * (Vs - Vm) : 0.0))
                                       : ((haveP ? 0.5 * (Vm - Vs) : 0.0) + 0.5 * (Vs - Vn));
@@ -336,9 +348,9 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
         if (blk == 0) { v[0] = c0; v[1] = c1; } else { v[2] = c0; v[3] = c1; }
       }
       block_sum4<T>(v, S.red);
-      const double Vp_ = pow_ndim(X[n1 - 1], ndim), Vq_ = pow_ndim(X[rb], ndim);
-      const double wp = 0.5 * (Vq_ - Vp_) + 0.5 * (Vp_ - pow_ndim(X[n1 - 2], ndim));
-      const double wq = 0.5 * (pow_ndim(X[rb + 1], ndim) - Vq_) + 0.5 * (Vq_ - Vp_);
+      const double Vp_ = powd<NDIM>(X[n1 - 1]), Vq_ = powd<NDIM>(X[rb]);
+      const double wp = 0.5 * (Vq_ - Vp_) + 0.5 * (Vp_ - powd<NDIM>(X[n1 - 2]));
+      const double wq = 0.5 * (powd<NDIM>(X[rb + 1]) - Vq_) + 0.5 * (Vq_ - Vp_);
       bif = (S.Mass0 - (v[0] + v[2])) / ((v[1] + wp) * S.KD + (v[3] + wq));
       aif = S.KD * bif;
     }
@@ -505,9 +517,9 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
       if ((A.flags & F_RECORD) && A.rec) {
         double v[4] = {0.0, 0.0, 0.0, 0.0};
         for (int i = tid; i < nr1 - 1; i += T)
-          v[0] += 0.5 * (S.rho1 * pow_ndim(X[i + 1], ndim) - S.rho1 * pow_ndim(X[i], ndim)) * (C[i] + C[i + 1]);
+          v[0] += 0.5 * (S.rho1 * powd<NDIM>(X[i + 1]) - S.rho1 * powd<NDIM>(X[i])) * (C[i] + C[i + 1]);
         for (int i = tid; i < nr2 - 1; i += T)
-          v[1] += 0.5 * (S.rho2 * pow_ndim(X[RB0 + i + 1], ndim) - S.rho2 * pow_ndim(X[RB0 + i], ndim)) * (C[RB0 + i] + C[RB0 + i + 1]);
+          v[1] += 0.5 * (S.rho2 * powd<NDIM>(X[RB0 + i + 1]) - S.rho2 * powd<NDIM>(X[RB0 + i])) * (C[RB0 + i] + C[RB0 + i + 1]);
         block_sum4<T>(v, S.red);
         if (tid == 0 && S.it >= 1 && S.it - 1 < A.rec_cap) {
           double *r = A.rec + ((size_t)mem * (size_t)A.rec_cap + (size_t)(S.it - 1)) * 4;
@@ -528,9 +540,9 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
     if ((A.flags & F_MASS_FINAL) && A.Mass) {
       double v[4] = {0.0, 0.0, 0.0, 0.0};
       for (int i = tid; i < n1 - 1; i += T)
-        v[0] += 0.5 * (S.rho1 * pow_ndim(X[i + 1], ndim) - S.rho1 * pow_ndim(X[i], ndim)) * (C[i] + C[i + 1]);
+        v[0] += 0.5 * (S.rho1 * powd<NDIM>(X[i + 1]) - S.rho1 * powd<NDIM>(X[i])) * (C[i] + C[i + 1]);
       for (int i = tid; i < n2 - 1; i += T)
-        v[1] += 0.5 * (S.rho2 * pow_ndim(X[rb + i + 1], ndim) - S.rho2 * pow_ndim(X[rb + i], ndim)) * (C[rb + i] + C[rb + i + 1]);
+        v[1] += 0.5 * (S.rho2 * powd<NDIM>(X[rb + i + 1]) - S.rho2 * powd<NDIM>(X[rb + i])) * (C[rb + i] + C[rb + i + 1]);
       block_sum4<T>(v, S.red);
       if (tid == 0) A.Mass[mem] = v[0] + v[1];
     }

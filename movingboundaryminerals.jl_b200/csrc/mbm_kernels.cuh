@@ -417,7 +417,7 @@ __device__ inline void chain_build(Scal &S, const KArgs &A, const MemberPtrs &P,
 }
 
 // ---- pchip slope at node i of one phase (functions.jl:786-806; value code, contraction allowed) ------
-__device__ __forceinline__ double pchip_slope(const double *x, const double *y, int n, int i) {
+__device__ __noinline__ double pchip_slope(const double *x, const double *y, int n, int i) {
   if (i == 0) {
     const double h1 = x[1] - x[0], h2 = x[2] - x[1];
     const double m1 = (y[1] - y[0]) * (1.0 / h1), m2 = (y[2] - y[1]) * (1.0 / h2);
@@ -484,7 +484,7 @@ __device__ __forceinline__ double pchip_slope_fast(const double *x, const double
 }
 // pchip evaluation with an interval search that walks from `guess` (count of old nodes below Xj);
 // identical branch/index semantics as pchip_eval_one (functions.jl:809-837)
-__device__ __forceinline__ double pchip_eval_walk(const double *x, const double *y, const double *d, int n, double Xj,
+__device__ __noinline__ double pchip_eval_walk(const double *x, const double *y, const double *d, int n, double Xj,
                                                   int guess, int *cout, int *kout, int *branch) {
   int c = min(max(guess, 0), n);
   int steps = 0;
@@ -525,13 +525,13 @@ __device__ __forceinline__ void reduced_solve(double *rs, double *rd, double *ru
   double bA = 0.0, bG = -1.0, bR0 = 0.0, bR1 = 0.0;
   if (RPL > 1) {
     int g = g0 + RPL - 2;
-    double inv = 1.0 / rd[g];
+    double inv = frcp_(rd[g]);
     bA = rs[g] * inv; bG = ru[g] * inv; bR0 = r0[g] * inv; bR1 = r1[g] * inv;
 #pragma unroll
     for (int k = RPL - 3; k >= 0; --k) {
       g = g0 + k;
       const double e = ru[g];
-      inv = 1.0 / (rd[g] - e * bA);
+      inv = frcp_(rd[g] - e * bA);
       bA = rs[g] * inv;
       bG = -e * bG * inv;
       bR0 = (r0[g] - e * bR0) * inv;
@@ -540,13 +540,13 @@ __device__ __forceinline__ void reduced_solve(double *rs, double *rd, double *ru
   }
   // pass 1 (forward): every row in terms of previous separator and next row
   {
-    double inv = 1.0 / rd[g0];
+    double inv = frcp_(rd[g0]);
     A[0] = rs[g0] * inv; G[0] = ru[g0] * inv; R0[0] = r0[g0] * inv; R1[0] = r1[g0] * inv;
 #pragma unroll
     for (int k = 1; k < RPL; ++k) {
       const int g = g0 + k;
       const double sb = rs[g];
-      inv = 1.0 / (rd[g] - sb * G[k - 1]);
+      inv = frcp_(rd[g] - sb * G[k - 1]);
       A[k] = -sb * A[k - 1] * inv;
       G[k] = ru[g] * inv;
       R0[k] = (r0[g] - sb * R0[k - 1]) * inv;
@@ -560,7 +560,7 @@ __device__ __forceinline__ void reduced_solve(double *rs, double *rd, double *ru
   {
     const double Gl = (lane == 31) ? 0.0 : G[RPL - 1];
     const double dg = 1.0 - Gl * nA;
-    const double inv = 1.0 / dg;
+    const double inv = frcp_(dg);
     ps = A[RPL - 1] * inv;
     pu = -Gl * nG * inv;
     p0 = (R0[RPL - 1] - Gl * nR0) * inv;
@@ -578,7 +578,7 @@ __device__ __forceinline__ void reduced_solve(double *rs, double *rd, double *ru
     if (lane < d) { ls = 0.0; lu = 0.0; l0 = 0.0; l1 = 0.0; }
     if (lane + d > 31) { hs = 0.0; hu = 0.0; h0 = 0.0; h1 = 0.0; }
     const double dg = 1.0 - ps * lu - pu * hs;
-    const double inv = 1.0 / dg;
+    const double inv = frcp_(dg);
     const double n0 = (p0 - ps * l0 - pu * h0) * inv;
     const double n1 = (p1 - ps * l1 - pu * h1) * inv;
     const double ns = -ps * ls * inv;
