@@ -218,3 +218,17 @@ def test_c4_shape_small_sample(oracle, cuda_lib):
     assert np.array_equal(eo.x_left, eg.x_left) and np.array_equal(eo.x_right, eg.x_right)
     assert eo.run(oracle, max_steps=30) == 0 and eg.run(cuda_lib, max_steps=30) == 0
     compare(eo, eg)
+
+
+def test_multi_device_sharding(oracle, cuda_lib):
+    """n_devices = 2 inside one call: contiguous member blocks, one host thread + stream per device"""
+    if cuda_lib.mbm_device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    pars = []
+    for k in range(7):
+        p = d.pars_MB_growth(); p.update(V_ip=(-1) ** k * (1 + 0.1 * k) * 1e-7, res=[60 + 5 * k, 90]); pars.append(p)
+    eo, _ = d.build_couple_ensemble(pars, oracle)
+    eg, _ = d.build_couple_ensemble(pars, cuda_lib)
+    assert eo.run(oracle, max_steps=80) == 0
+    assert eg.run(cuda_lib, max_steps=80, n_devices=2) == 0
+    compare(eo, eg)
