@@ -259,42 +259,46 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
       }
       double Qb = 0.0, Vm = 0.0, Vs = 0.0;
       if (mb) { Vs = powd<NDIM>(x_self); Vm = haveP ? powd<NDIM>(x_prev) : Vs; }
-      for (int k = 0; k < len; ++k) {
-        const int ell = f + k;
-        const int s = ST(ell);
-        const double x_next = X[ST(ell + 1)];
-        const double c_next = (k == len - 1) ? c_halo_next : C[ST(ell + 1)];
-        double A11, A12, A22, kk, nAself, nAnext;
-        if (sdir > 0) { elem_mats_fast<NDIM>(x_self, x_next, Dph, idt, A11, A12, A22, kk); nAself = A11; nAnext = A22; }
-        else { elem_mats_fast<NDIM>(x_next, x_self, Dph, idt, A11, A12, A22, kk); nAself = A22; nAnext = A11; }
-        double diag = (nAself - kk) + (haveP ? (pAnext - pkk) : 0.0);
-        double rhs = (nAself * c_self + A12 * c_next) + (haveP ? (pAc * c_prev + pAnext * c_self) : 0.0);
-        double sup = A12 + kk;
-        double sub = haveP ? (pAc + pkk) : 0.0;
-        if (ell == 0 && dir0) { diag = 1.0; rhs = blk ? Co_last : Co_first; sup = 0.0; sub = 0.0; }
-        const double inv = frcp(diag - sub * Gp);
-        const double An = (k == 0) ? (sub * inv) : (-sub * Ap * inv);
-        const double Gn = sup * inv;
-        const double Rn = (rhs - sub * Rp) * inv;
+      const int s0 = ST(f);
 #pragma unroll
-        for (int kk2 = 0; kk2 < MAXM; ++kk2) if (kk2 == k) Areg[kk2] = An;
-        W[s] = Gn; C[s] = Rn;
-        if (mb) {
-          const double Vn = powd<NDIM>(x_next);
-          // trapezoid weight 0.5*(V[g+1]-V[g]) + 0.5*(V[g]-V[g-1]) in global order (functions.jl:291-296)
-          const double w = (sdir > 0) ? (0.5 * (Vn - Vs) + (haveP ? 0.5 * (Vs - Vm) : 0.0))
-                                      : ((haveP ? 0.5 * (Vm - Vs) : 0.0) + 0.5 * (Vs - Vn));
-          if (k < len - 1) {
-            const double tq = Qb + w;
-            P0 = fma(tq, Rn, P0);
-            Qa = fma(-tq, An, Qa);
-            Qb = -tq * Gn;
-          } else Qc = Qb + w;
-          Vm = Vs; Vs = Vn;
+      for (int k = 0; k < MAXM; ++k) {
+        if (k < len) {
+          const int ell = f + k;
+          const int s = s0 + ((sdir > 0) ? k : -k);
+          const int sn = s + sdir;
+          const double x_next = X[sn];
+          const double c_next = (k == len - 1) ? c_halo_next : C[sn];
+          double A11, A12, A22, kk, nAself, nAnext;
+          if (sdir > 0) { elem_mats_fast<NDIM>(x_self, x_next, Dph, idt, A11, A12, A22, kk); nAself = A11; nAnext = A22; }
+          else { elem_mats_fast<NDIM>(x_next, x_self, Dph, idt, A11, A12, A22, kk); nAself = A22; nAnext = A11; }
+          double diag = (nAself - kk) + (haveP ? (pAnext - pkk) : 0.0);
+          double rhs = (nAself * c_self + A12 * c_next) + (haveP ? (pAc * c_prev + pAnext * c_self) : 0.0);
+          double sup = A12 + kk;
+          double sub = haveP ? (pAc + pkk) : 0.0;
+          if (ell == 0 && dir0) { diag = 1.0; rhs = blk ? Co_last : Co_first; sup = 0.0; sub = 0.0; }
+          const double inv = frcp(diag - sub * Gp);
+          const double An = (k == 0) ? (sub * inv) : (-sub * Ap * inv);
+          const double Gn = sup * inv;
+          const double Rn = (rhs - sub * Rp) * inv;
+          Areg[k] = An;
+          W[s] = Gn; C[s] = Rn;
+          if (mb) {
+            const double Vn = powd<NDIM>(x_next);
+            // trapezoid weight 0.5*(V[g+1]-V[g]) + 0.5*(V[g]-V[g-1]) in global order (functions.jl:291-296)
+            const double w = (sdir > 0) ? (0.5 * (Vn - Vs) + (haveP ? 0.5 * (Vs - Vm) : 0.0))
+                                        : ((haveP ? 0.5 * (Vm - Vs) : 0.0) + 0.5 * (Vs - Vn));
+            if (k < len - 1) {
+              const double tq = Qb + w;
+              P0 = fma(tq, Rn, P0);
+              Qa = fma(-tq, An, Qa);
+              Qb = -tq * Gn;
+            } else Qc = Qb + w;
+            Vm = Vs; Vs = Vn;
+          }
+          Ap = An; Gp = Gn; Rp = Rn;
+          x_prev = x_self; c_prev = c_self; x_self = x_next; c_self = c_next;
+          pAc = A12; pAnext = nAnext; pkk = kk; haveP = true;
         }
-        Ap = An; Gp = Gn; Rp = Rn;
-        x_prev = x_self; c_prev = c_self; x_self = x_next; c_self = c_next;
-        pAc = A12; pAnext = nAnext; pkk = kk; haveP = true;
       }
       // ---- backward accumulate: first row of the chunk in terms of the two separators ----
       double bA = 0.0, bG = -1.0, bR = 0.0;
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
 #pragma unroll
         for (int k = MAXM - 2; k >= 0; --k) {
           if (k < len - 1) {
-            const int s = ST(f + k);
+            const int s = s0 + ((sdir > 0) ? k : -k);
             const double Gk = W[s], Rk = C[s], Ak = Areg[k];
             if (first) { bA = Ak; bG = Gk; bR = Rk; first = false; }
             else { bR = Rk - Gk * bR; bA = Ak - Gk * bA; bG = -Gk * bG; }
@@ -375,17 +379,16 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
     __syncthreads();
 #undef ST
 
-    // =========================== regrid: new meshes + pchip, in registers ===========================
+    // =========================== regrid: new meshes + pchip ===========================
     {
       const int nr1 = S.nr1, nr2 = S.nr2;
       const double Ri1 = S.Ri1;
-      const double *xl_o = X, *yl_o = C, *dl_o = W, *xr_o = X + rb, *yr_o = C + rb, *dr_o = W + rb;
-      // phase 1: slopes of the old profiles (interleaved nodes) | local scans of the new mesh spacings
-      for (int i = tid; i < n1; i += T) W[i] = pchip_slope_fast(xl_o, yl_o, n1, i);
-      for (int i = tid; i < n2; i += T) W[rb + i] = pchip_slope_fast(xr_o, yr_o, n2, i);
+      const double *xl_o = X, *yl_o = C, *xr_o = X + rb, *yr_o = C + rb;
+      // ---- phase A: new meshes by the canonical scans (one tile of 9 elements per thread and phase), staged in W
+      //      (W is free here: the slopes of the old profiles are computed on the fly during the evaluation)
       const int nl = nr1 - 1, nrr = nr2 - 1;
-      const int e0 = tid * CSO_TILE;                      // first element of this thread's tile (both phases)
-      double xnL[CSO_TILE], xnR[CSO_TILE];
+      const int e0 = tid * CSO_TILE;
+      double tl[CSO_TILE], tr[CSO_TILE];
       double incL, incR;
       {
         const double bR = xmul(1.0, xinv(S.MRefin));
@@ -394,7 +397,7 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
         for (int k = 0; k < CSO_TILE; ++k) {
           const int i = e0 + k;
           if (i < nl) { const double v = linrange_at(1.0, bR, nl, i); s = (k == 0) ? v : xadd(s, v); }
-          xnL[k] = s;
+          tl[k] = s;
         }
         incL = s;
         const double Rt = S.newton_R, d = S.grid_d;
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
         for (int k = 0; k < CSO_TILE; ++k) {
           const int i = e0 + k;
           if (i < nrr) { const double v = (i == 0) ? d : Rt; pr = (k == 0) ? v : xmul(pr, v); }
-          xnR[k] = pr;
+          tr[k] = pr;
         }
         incR = pr;
 #pragma unroll
@@ -416,7 +419,6 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
       if (tid == 0 && S.rec_status) S.status = S.rec_status;      // Newton failure raised inside regrid!
       __syncthreads();
       if (S.status != 0) break;
-      // phase 2: finish left mesh and right spacings; local sum scan of the right spacings
       double incS;
       {
         const double EqL = __shfl_up_sync(0xffffffffu, incL, 1), EqR = __shfl_up_sync(0xffffffffu, incR, 1);
@@ -426,14 +428,15 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
         double s = 0.0;
 #pragma unroll
         for (int k = 0; k < CSO_TILE; ++k) {
-          double cs = (lane == 0) ? xnL[k] : xadd(EqL, xnL[k]);
+          double cs = (lane == 0) ? tl[k] : xadd(EqL, tl[k]);
           if (wid > 0) cs = xadd(OgL, cs);
-          xnL[k] = xmul(xmul(cs, Ri1), isum);                                   // X_left[e0+k+1]
-          double dx = (lane == 0) ? xnR[k] : xmul(EqR, xnR[k]);
+          if (e0 + k < nl) W[e0 + k + 1] = xmul(xmul(cs, Ri1), isum);             // X_left[e0+k+1]
+          double dx = (lane == 0) ? tr[k] : xmul(EqR, tr[k]);
           if (wid > 0) dx = xmul(OgR, dx);
           if (e0 + k < nrr) s = (k == 0) ? dx : xadd(s, dx);
-          xnR[k] = s;
+          tr[k] = s;
         }
+        if (tid == 0) W[0] = xmul(xmul(0.0, Ri1), isum);
         incS = s;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -443,72 +446,47 @@ __global__ void __launch_bounds__(T, 2) mbm_step_kernel_v2(const KArgs A, const 
         if (lane == 31) gtotC[wid] = incS;
       }
       __syncthreads();
-      // phase 3: finish right mesh; evaluate pchip on the left mesh
-      double PL[CSO_TILE], P_first = 0.0;
       {
         const double EqS = __shfl_up_sync(0xffffffffu, incS, 1);
         double OgS = 0.0;
         if (wid > 0) { OgS = gtotC[0]; for (int g = 1; g < wid; ++g) OgS = xadd(OgS, gtotC[g]); }
 #pragma unroll
         for (int k = 0; k < CSO_TILE; ++k) {
-          double cs = (lane == 0) ? xnR[k] : xadd(EqS, xnR[k]);
+          double cs = (lane == 0) ? tr[k] : xadd(EqS, tr[k]);
           if (wid > 0) cs = xadd(OgS, cs);
-          xnR[k] = xadd(Ri1, cs);                                                // X_right[e0+k+1]
+          if (e0 + k < nrr) W[RB0 + e0 + k + 1] = xadd(Ri1, cs);                   // X_right[e0+k+1]
         }
-        int c = -1;
+        if (tid == 0) W[RB0] = Ri1;
+      }
+      __syncthreads();
+      // ---- phase B: evaluate the old profiles on the new meshes, nodes interleaved over all threads
+      const int ntot = nr1 + nr2;
+      const float ratL = (float)n1 / (float)nr1, ratR = (float)n2 / (float)nr2;
+      double Pq[MAXM];
 #pragma unroll
-        for (int k = 0; k < CSO_TILE; ++k) {
-          const int j = e0 + k + 1;
-          if (j < nr1) {
-            int kk, br;
-            PL[k] = pchip_eval_walk(xl_o, yl_o, dl_o, n1, xnL[k], (c < 0) ? (int)(((long long)j * n1) / nr1) : c, &c, &kk, &br);
-            if (do_hash) hash_local += idx_term(S.it, 0, j, kk, br);
-          }
-        }
-        if (tid == T - 1) {   // node 0 of the left mesh: X = 0*Ri1*isum
-          int kk, br, cc;
-          const double x0 = xmul(xmul(0.0, Ri1), xinv(S.ch.csA));
-          P_first = pchip_eval_walk(xl_o, yl_o, dl_o, n1, x0, 0, &cc, &kk, &br);
-          if (do_hash) hash_local += idx_term(S.it, 0, 0, kk, br);
+      for (int q = 0; q < MAXM; ++q) {
+        const int j = tid + q * T;
+        if (j < ntot) {
+          const bool left = j < nr1;
+          const int jj = left ? j : (j - nr1);
+          const double Xj = W[left ? jj : (RB0 + jj)];
+          int kk, br;
+          Pq[q] = pchip_eval_otf(left ? xl_o : xr_o, left ? yl_o : yr_o, left ? n1 : n2, Xj,
+                                 __float2int_rd((float)jj * (left ? ratL : ratR)), &kk, &br);
+          if (do_hash) hash_local += idx_term(S.it, left ? 0 : 1, jj, kk, br);
         }
       }
       __syncthreads();
-      // phase 4: write the left phase; evaluate pchip on the right mesh
-      double PR[CSO_TILE], PR_first = 0.0;
-      {
+      // ---- phase C: commit the new meshes and profiles
 #pragma unroll
-        for (int k = 0; k < CSO_TILE; ++k) {
-          const int j = e0 + k + 1;
-          if (j < nr1) { X[j] = xnL[k]; C[j] = PL[k]; }
-        }
-        if (tid == T - 1) { X[0] = xmul(xmul(0.0, Ri1), xinv(S.ch.csA)); C[0] = P_first; }
-        int c = -1;
-#pragma unroll
-        for (int k = 0; k < CSO_TILE; ++k) {
-          const int j = e0 + k + 1;
-          if (j < nr2) {
-            int kk, br;
-            PR[k] = pchip_eval_walk(xr_o, yr_o, dr_o, n2, xnR[k], (c < 0) ? (int)(((long long)j * n2) / nr2) : c, &c, &kk, &br);
-            if (do_hash) hash_local += idx_term(S.it, 1, j, kk, br);
-          }
-        }
-        if (tid == T - 1) {   // node 0 of the right mesh: X = Ri1
-          int kk, br, cc;
-          PR_first = pchip_eval_walk(xr_o, yr_o, dr_o, n2, Ri1, 0, &cc, &kk, &br);
-          if (do_hash) hash_local += idx_term(S.it, 1, 0, kk, br);
+      for (int q = 0; q < MAXM; ++q) {
+        const int j = tid + q * T;
+        if (j < ntot) {
+          const int sidx = (j < nr1) ? j : (RB0 + j - nr1);
+          X[sidx] = W[sidx]; C[sidx] = Pq[q];
         }
       }
-      __syncthreads();
-      // phase 5: write the right phase at its home position
-      {
-#pragma unroll
-        for (int k = 0; k < CSO_TILE; ++k) {
-          const int j = e0 + k + 1;
-          if (j < nr2) { X[RB0 + j] = xnR[k]; C[RB0 + j] = PR[k]; }
-        }
-        if (tid == T - 1) { X[RB0] = Ri1; C[RB0] = PR_first; }
-        if (tid == 0) { S.n1 = nr1; S.n2 = nr2; S.gap = RB0; }
-      }
+      if (tid == 0) { S.n1 = nr1; S.n2 = nr2; S.gap = RB0; }
       steps_done += 1;
       __syncthreads();
       if (tid == 0) {
