@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Measure the other BASELINE.json configurations (c2a, c2b, c3, c5) once on a B200 and check a subset of
+every ensemble against the CPU oracle.  These are parity-test cases, not bench lines (bench.py measures c4);
+the numbers go to profiles/ as a record of where each kernel variant stands."""
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import mbm_b200  # noqa: E402
+from mbm_b200 import abi, drivers as d, ensembles as E  # noqa: E402
+from oracle import load as oracle_load  # noqa: E402
+
+
+def relerr(a, b):
+    den = np.max(np.abs(a))
+    return 0.0 if den == 0 else float(np.max(np.abs(a - b)) / den)
+
+
+def run(name, gen, build, M, max_steps, n_check, flags=0, tol=1e-10, ints=True):
+    cuda, ora = mbm_b200.load_cuda_library(), oracle_load.load()
+    pars = gen(M)
+    t0 = time.perf_counter()
+    eg = build(cuda, pars)
+    tb = time.perf_counter() - t0
+    eo = build(ora, pars[:n_check])      # the same first members through the oracle
+    t0 = time.perf_counter()
+    rc = eg.run(cuda, max_steps=max_steps, flags=flags)
+    te = time.perf_counter() - t0
+    ks = cuda.mbm_last_kernel_seconds()
+    assert rc == 0, rc
+    t0 = time.perf_counter()
+    assert eo.run(ora, max_steps=max_steps) == 0
+    tc = time.perf_counter() - t0
+    worst = 0.0
+    for m in range(n_check):
+        for a, b in zip(eo.member(m), eg.member(m)):
+            worst = max(worst, relerr(a, b))
+    ok_int = bool(np.array_equal(eo.res, eg.res[:n_check]) and np.array_equal(eo.it, eg.it[:n_check]) and
+                  np.array_equal(eo.status, eg.status[:n_check]))
+    if ints:
+        ok_int = ok_int and bool(np.array_equal(eo.idx_hash, eg.idx_hash[:n_check]))
+    ns = int(eg.node_steps.sum())
+    out = {"config": name, "members": M, "max_steps": max_steps, "node_steps": ns, "kernel_s": ks, "e2e_s": te,
+           "node_steps_per_s_kernel": ns / ks if ks > 0 else None, "node_steps_per_s_e2e": ns / te,
+           "members_failed": int((eg.status != 0).sum()), "parity_members": n_check, "parity_max_relerr": worst,
+           "parity_integers_exact": ok_int, "oracle_node_steps_per_s": int(eo.node_steps.sum()) / tc,
+           "build_s": tb}
+    print(json.dumps(out), flush=True)
+    assert worst < tol, (name, worst)
+    assert ok_int, name
+    return out
+
+
+def main():
+    which = sys.argv[1:] or ["c2a", "c2b", "c3", "c5"]
+    res = []
+    if "c2a" in which:   # examples/C1.jl sweep, 4096 members, whole run (~18k steps each) is long: 2000 steps
+        res.append(run("c2a: C1 MB/Rayleigh sweep, res [80 120]", E.c2a_rayleigh_sweep, lambda lib, P: d.build_couple_ensemble(P, lib)[0],
+                       4096, 2000, 4))
+    if "c2b" in which:
+        res.append(run("c2b: Stefan sweep, res [15 25]", E.c2b_stefan_sweep, lambda lib, P: d.build_stefan_ensemble(P, lib),
+                       4096, 2000, 4, tol=1e-8, ints=False))
+    if "c3" in which:
+        res.append(run("c3: flux fixed interface, n=256/phase", lambda M: E.c3_flux_fixed(M, 256), lambda lib, P: d.build_couple_ensemble(P, lib)[0],
+                       16384, 1000, 4))
+    if "c5" in which:
+        res.append(run("c5: MB growth n=65536/phase MRefin=1 (global-memory variant)",
+                       lambda M: E.c5_highres(M, 65536, max_steps=100),
+                       lambda lib, P: d.build_couple_ensemble(P, lib, cap_left=65540, cap_right=65540)[0],
+                       64, 20, 1, tol=1e-9))
+    (ROOT / "gpurun_out").mkdir(exist_ok=True)
+    (ROOT / "gpurun_out" / "configs.json").write_text(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()
