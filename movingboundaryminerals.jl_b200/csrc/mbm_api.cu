@@ -110,11 +110,9 @@ int launch_T(const mbm::KArgs &A, int member0, int count, bool use_global, size_
   return (cudaGetLastError() == cudaSuccess) ? 0 : MBM_RC_CUDA;
 }
 
-constexpr int V2_MAXM = 15;
-
 template <int T, int NDIM>
 int launch_v2_TN(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
-  auto kern = mbm::mbm_step_kernel_v2<T, V2_MAXM, NDIM>;
+  auto kern = mbm::mbm_step_kernel_v2<T, NDIM>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return MBM_RC_CUDA;
   kern<<<count, T, smem_bytes, s>>>(A, member0);
@@ -129,31 +127,24 @@ int launch_v2_T(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, 
   }
 }
 
-// shared-memory capacities of the tuned kernel: as large as the caps allow within (a) two CTAs per SM,
-// (b) one scan tile per thread per phase (9*T elements), (c) at most V2_MAXM rows per thread in the solve
-void v2_plan(int capL, int capR, int smem_per_sm, int *T2, int *kL, int *kR) {
-  int kl = capL, kr = capR;
-  if (const char *e = getenv("MBM_KCAP")) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2) { kl = a < capL ? a : capL; kr = b < capR ? b : capR; } }
-  const int each_max = 9 * 256 + 1;
-  if (kl > each_max) kl = each_max;
-  if (kr > each_max) kr = each_max;
+// combined shared-memory capacity (left | free slot | right) of the tuned kernel: as large as the caps need, within
+// two CTAs per SM (four arrays of kS doubles) and one scan tile per thread and phase (9*T nodes per phase)
+void v2_plan(int capL, int capR, int smem_per_sm, int *T2, int *kS) {
+  int ks = capL + capR + 1;
+  if (const char *e = getenv("MBM_KCAP")) { const int a = atoi(e); if (a >= 8 && a < ks) ks = a; }
   const int static_est = (int)sizeof(mbm::Scal) + 8 * 256 * 8 + 3 * 16 * 8 + 64;
   const int per_cta = (smem_per_sm - 2 * 1024) / 2 - static_est;
-  int sum_max = per_cta / (3 * 8) - 1;
-  const int rows_max = (256 - 2) * V2_MAXM;
-  if (sum_max > rows_max) sum_max = rows_max;
-  if (kl + kr > sum_max) {
-    const double f = (double)sum_max / (double)(kl + kr);
-    kl = (int)(kl * f); kr = sum_max - kl;
-  }
+  int ks_max = per_cta / (4 * 8);
+  ks_max -= ks_max % 8;
+  if (ks > ks_max) ks = ks_max;
   int T = 256;
-  if (kl <= 9 * 64 + 1 && kr <= 9 * 64 + 1 && kl + kr <= (64 - 2) * V2_MAXM) T = 64;
-  else if (kl <= 9 * 128 + 1 && kr <= 9 * 128 + 1 && kl + kr <= (128 - 2) * V2_MAXM) T = 128;
+  if (ks <= 9 * 64) T = 64;
+  else if (ks <= 9 * 128) T = 128;
   if (const char *e = getenv("MBM_V2_THREADS")) {
     const int t = atoi(e);
-    if ((t == 64 || t == 128 || t == 256) && kl <= 9 * t + 1 && kr <= 9 * t + 1 && kl + kr <= (t - 2) * V2_MAXM) T = t;
+    if (t == 64 || t == 128 || t == 256) T = t;
   }
-  *T2 = T; *kL = kl; *kR = kr;
+  *T2 = T; *kS = ks;
 }
 
 size_t static_smem_for(int T) { return sizeof(mbm::Scal) + 8 * (size_t)T * sizeof(double) + 256; }
@@ -190,8 +181,9 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
   if (use_v2) {
     int smem_sm = 0;
     CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
-    v2_plan(A.capL, A.capR, smem_sm, &T2, &A.kcapL, &A.kcapR);
-    if (A.kcapL < 4 || A.kcapR < 4) use_v2 = false;
+    v2_plan(A.capL, A.capR, smem_sm, &T2, &A.kcapL);
+    A.kcapR = 0;
+    if (A.kcapL < 8) use_v2 = false;
   }
   if (couple_pv && !getenv("MBM_NO_CHAIN")) {
     const int Tr = (use_v2 && T2 > T) ? T2 : T;
@@ -216,7 +208,7 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
     int rc;
     if (use_v2) {
       // tuned kernel first; the general kernel then only continues members handed over with status -1
-      const size_t dyn2 = 3 * (size_t)(A.kcapL + 1 + A.kcapR) * sizeof(double);
+      const size_t dyn2 = 4 * (size_t)A.kcapL * sizeof(double);
       mbm::KArgs A2 = A;
       A2.only_deferred = 0;
       switch (T2) {

@@ -341,8 +341,10 @@ __device__ inline int chain_update_params(const Scal &S, const KArgs &A, const M
 
 // thread 0: advance the scalar chain by up to `maxrec` steps, writing one record per step.
 // Same operations, in the same order, as step_scalars + the closed-form mesh scalars of define_new_grid.
+// capL/capR: array capacities (exceeding them is the hard status 10); capS / capPhase: capacity of the calling
+// kernel's shared-memory layout (exceeding them is the soft code 13: the member is handed to the general kernel)
 __device__ inline void chain_build(Scal &S, const KArgs &A, const MemberPtrs &P, double *recs, int maxrec, int capL,
-                                   int capR) {
+                                   int capR, int capS, int capPhase) {
   Chain &c = S.ch;
   c.count = 0; c.pos = 0;
   const double V = S.V;
@@ -386,6 +388,7 @@ __device__ inline void chain_build(Scal &S, const KArgs &A, const MemberPtrs &P,
       if (nr1 < S.resmin1) nr1 = S.resmin1;
       if (nr2 < S.resmin2) nr2 = S.resmin2;
       if (nr1 > capL || nr2 > capR || nr1 < 3 || nr2 < 3) rc = 10;
+      else if (n1s + n2s > capS || nr1 + nr2 + 1 > capS || nr1 > capPhase || nr2 > capPhase) rc = 13;
     }
     if (!rc && (int)nr1 - 1 != c.cs_nl) {      // left scan totals for this node count not cached: pause
       c.need_scan = 1; c.scan_nl = (int)nr1 - 1;
@@ -795,7 +798,7 @@ __global__ void __launch_bounds__(T) mbm_step_kernel(const KArgs A, const int me
           if (tid == 0) { S.ch.csA = Xn[nl - 1]; S.ch.csB = Xn[nl - 2]; S.ch.cs_nl = nl; S.ch.need_scan = 0; }
           cta_sync<T>();
         }
-        if (tid == 0) chain_build(S, A, P, recs, T, A.capL, A.capR);
+        if (tid == 0) chain_build(S, A, P, recs, T, A.capL, A.capR, 0x7fffffff, 0x7fffffff);
         cta_sync<T>();
         const int cnt = S.ch.count;
         lcount = cnt; lpos = 0;

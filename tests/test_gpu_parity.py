@@ -190,7 +190,7 @@ def test_streaming_kernel_matches_resident(cuda_lib):
 def test_handover_to_general_kernel(oracle, cuda_lib, monkeypatch):
     """members that outgrow the tuned kernel's shared-memory capacity are handed over (status -1) to the general
     kernel mid-call and finish there; the result is the same as the oracle's"""
-    monkeypatch.setenv("MBM_KCAP", "70,100")
+    monkeypatch.setenv("MBM_KCAP", "170")
     pars = []
     for V, res in ((-1e-7, [60, 90]), (1e-7, [60, 90]), (-1e-7, [40, 60]), (2e-7, [30, 40])):
         p = d.pars_MB_growth(); p.update(V_ip=V, res=res); pars.append(p)
