@@ -191,6 +191,8 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
     if (!A.recs) return st->rc ? st->rc : MBM_RC_OOM;
   }
   if (use_v2) {
+    A.csbuf = (double *)st->scratch((size_t)chunk * (size_t)(9 * T2 + 8) * sizeof(double));
+    if (!A.csbuf) return st->rc ? st->rc : MBM_RC_OOM;
     A.steps_done = (long long *)st->scratch((size_t)count * sizeof(long long));
     if (!A.steps_done) return st->rc ? st->rc : MBM_RC_OOM;
     CK(cudaMemsetAsync(A.steps_done, 0, (size_t)count * sizeof(long long), s));

@@ -41,6 +41,7 @@ struct KArgs {
   double *rec;
   double *s_D;  // simple: io.D
   double *recs; // run-ahead step records: gridDim * T * REC_N doubles (global, L2 resident)
+  double *csbuf;          // tuned kernel: gridDim * (9*T + 8) doubles, cached canonical scan of the left mesh spacings
   long long *steps_done;  // [M] steps completed in this call by the tuned kernel (hand-over to the general kernel)
   int kcapL, kcapR;       // shared-memory capacities of the tuned kernel
   int only_deferred, pad3_;  // general kernel: process only members handed over with status -1
@@ -518,32 +519,40 @@ __device__ __noinline__ double pchip_eval_walk(const double *x, const double *y,
 
 
 __device__ __forceinline__ double slope_interior(double ihm, double ihp, double mm, double mp) {
-  double d = (ihm * mm + ihp * mp) * frcp_(ihm + ihp);      // weights 2/h: the factor 2 cancels
-  if (mm * mp < 0.0 || mm == 0.0 || mp == 0.0) d = 0.0;
+  // d = (w- m- + w+ m+)/(w- + w+), w = 2/h (the factor 2 cancels); zero on sign change / zero secant; limiter 3*min|m|
+  const double d = (ihm * mm + ihp * mp) * frcp_(ihm + ihp);
   const double lim = 3.0 * fmin(fabs(mm), fabs(mp));
-  const double ad = fmin(fabs(d), lim);
-  return (d > 0.0) ? ad : ((d < 0.0) ? -ad : d);
+  const double ad = (mm * mp > 0.0) ? fmin(fabs(d), lim) : 0.0;
+  return copysign(ad, d);
 }
 // pchip evaluation of one new node with the two slopes of its interval computed on the fly
 // (functions.jl:786-837: same slopes, same branch/index semantics; no slope array needed)
-__device__ __noinline__ double pchip_eval_otf(const double *x, const double *y, int n, double Xj, int guess, int *kout,
-                                              int *branch) {
-  int c = min(max(guess, 0), n);
+__device__ __forceinline__ double pchip_eval_otf(const double *x, const double *y, int n, double Xj, int guess, int *kout,
+                                                 int *branch) {
+  // c = number of old nodes strictly below Xj, found by walking from the guess (xa = x[c-1], xb = x[c])
+  int c = min(max(guess, 1), n - 1);
+  double xa = x[c - 1], xb = x[c];
   int steps = 0;
-  bool ok = true;
-  while (c < n && x[c] < Xj) { ++c; if (++steps > 16) { ok = false; break; } }
-  if (ok) while (c > 0 && !(x[c - 1] < Xj)) { --c; if (++steps > 16) { ok = false; break; } }
-  if (!ok) {
+  while (xb < Xj && c < n) {
+    ++c; xa = xb; xb = (c < n) ? x[c] : xb;
+    if (++steps > 12) break;
+  }
+  while (!(xa < Xj) && c > 0 && steps <= 12) {
+    --c; xb = xa; xa = (c > 0) ? x[c - 1] : xa;
+    ++steps;
+  }
+  if (steps > 12) {
     int lo = 0, hi = n;
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (x[mid] < Xj) lo = mid + 1; else hi = mid; }
     c = lo;
+    xa = (c > 0) ? x[c - 1] : 0.0; xb = (c < n) ? x[c] : 0.0;
   }
-  if (c < n && x[c] == Xj) { *kout = c; *branch = 0; return y[c]; }
+  if (c < n && xb == Xj) { *kout = c; *branch = 0; return y[c]; }
   if (c == n) { *kout = n - 1; *branch = 1; return y[n - 1]; }
   if (c == 0) { *kout = 0; *branch = 2; return y[0]; }
   const int k = c - 1;
   *kout = k; *branch = 3;
-  const double x1 = x[k], x2 = x[k + 1], y1 = y[k], y2 = y[k + 1];
+  const double x1 = xa, x2 = xb, y1 = y[k], y2 = y[k + 1];
   const double h = x2 - x1;
   const double ih = frcp_(h), m1 = (y2 - y1) * ih;
   double d1, d2;
@@ -552,13 +561,12 @@ __device__ __noinline__ double pchip_eval_otf(const double *x, const double *y, 
   if (k + 1 == n - 1) d2 = pchip_slope(x, y, n, n - 1);
   else { const double ihp = frcp_(x[k + 2] - x2); d2 = slope_interior(ih, ihp, m1, (y[k + 2] - y2) * ihp); }
   const double s = Xj - x1;
-  const double ih2 = ih * ih, ih3 = ih2 * ih;
-  const double s2 = s * s, s3 = s2 * s, h3 = h * h * h, smh = s - h;
-  const double t1 = (3.0 * h * s2 - 2.0 * s3) * ih3 * y2;
-  const double t2 = (h3 - 3.0 * h * s2 + 2.0 * s3) * ih3 * y1;
-  const double t3 = (s2 * smh) * ih2 * d2;
-  const double t4 = (s * (smh * smh)) * ih2 * d1;
-  return t1 + t2 + t3 + t4;
+  const double u = s * ih;                    // s/h in [0,1]
+  const double smh = s - h;
+  // P = (3u^2 - 2u^3) y2 + (1 - 3u^2 + 2u^3) y1 + u^2 (s-h) d2 + u (s-h)^2/h d1
+  const double u2 = u * u;
+  const double w2 = u2 * (3.0 - 2.0 * u);
+  return w2 * y2 + (1.0 - w2) * y1 + (u2 * smh) * d2 + (u * smh) * (smh * ih) * d1;
 }
 
 // ---- reduced-system solve (levels 2 and 3): warp 0 solves the T-row tridiagonal system with two right-
