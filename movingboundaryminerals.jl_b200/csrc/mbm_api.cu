@@ -244,6 +244,19 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
   return 0;
 }
 
+// keep the stream-ordered allocator's memory cached between calls (default: released at the next synchronisation,
+// which re-maps hundreds of MB of scratch on every call)
+void keep_pool_cached(int device) {
+  static bool done[64] = {false};
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done[device] = true;
+}
+
 int check_common(const mbm_common *c) {
   if (!c || c->abi_version != MBM_ABI_VERSION) return MBM_RC_BAD_ARG;
   if (c->n_members < 0 || c->cap_left < 3 || c->hist_len < 2) return MBM_RC_BAD_ARG;
@@ -262,6 +275,7 @@ int check_common(const mbm_common *c) {
 int couple_shard(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io *io, int m0, int m1, int device,
                  double *ksec) {
   CK(cudaSetDevice(device));
+  keep_pool_cached(device);
   Stage st;
   st.device_ptrs = (c->flags & MBM_FLAG_DEVICE_POINTERS) != 0;
   const bool own_stream = !g_have_user_stream;
@@ -337,6 +351,7 @@ int couple_shard(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io 
 int simple_shard(const mbm_common *c, const mbm_simple_params *p, mbm_simple_io *io, int m0, int m1, int device,
                  double *ksec) {
   CK(cudaSetDevice(device));
+  keep_pool_cached(device);
   Stage st;
   st.device_ptrs = (c->flags & MBM_FLAG_DEVICE_POINTERS) != 0;
   const bool own_stream = !g_have_user_stream;

@@ -317,12 +317,26 @@ __device__ inline void step_scalars(Scal &S, const KArgs &A, const MemberPtrs &P
 
 
 // history lookup for the chain: same arithmetic as update_t_dependent, explicit state
-__device__ inline int chain_update_params(const Scal &S, const KArgs &A, const MemberPtrs &P, double t, int *cur,
+// history interval cache of the chain: the knots around t and the (correctly rounded) reciprocal of their distance
+struct HistCache { int i; double x0, x1, iv, k0, k1, T0, T1; };
+__device__ __forceinline__ void hist_load(HistCache &h, const MemberPtrs &P, int i) {
+  h.i = i; h.x0 = P.t_ar[i]; h.x1 = P.t_ar[i + 1]; h.iv = xinv(xsub(h.x1, h.x0));
+  h.k0 = P.KD_ar[i]; h.k1 = P.KD_ar[i + 1]; h.T0 = P.T_ar[i]; h.T1 = P.T_ar[i + 1];
+}
+// update_t_dependent_param! for the chain: same arithmetic as lin_interp_cursor / update_t_dependent
+__device__ inline int chain_update_params(const Scal &S, const KArgs &A, const MemberPtrs &P, double t, HistCache &h,
                                           double *KD, double *Tt, double *D_l, double *D_r) {
-  int rc = lin_interp_cursor(P.t_ar, P.KD_ar, A.hist_len, t, cur, S.tmin, S.tmax, KD);
-  if (rc) return rc;
-  rc = lin_interp_cursor(P.t_ar, P.T_ar, A.hist_len, t, cur, S.tmin, S.tmax, Tt);
-  if (rc) return rc;
+  if (t < S.tmin || t > S.tmax) return 6;
+  if (t > h.x1 || t < h.x0 || (t == h.x0 && h.i > 0)) {          // left the cached interval: walk the cursor
+    int i = h.i;
+    while (i + 2 < A.hist_len && t > P.t_ar[i + 1]) ++i;
+    while (i > 0 && t <= P.t_ar[i] && t >= P.t_ar[i - 1]) --i;
+    hist_load(h, P, i);
+  }
+  const double N2 = xmul(xsub(t, h.x0), h.iv);
+  const double N1 = xsub(1.0, N2);
+  *KD = xadd(xmul(N1, h.k0), xmul(N2, h.k1));
+  *Tt = xadd(xmul(N1, h.T0), xmul(N2, h.T1));
   if (t == S.t_tot) {
     *Tt = P.T_ar[A.hist_len - 1];
     *KD = P.KD_ar[A.hist_len - 1];
@@ -349,6 +363,11 @@ __device__ inline void chain_build(Scal &S, const KArgs &A, const MemberPtrs &P,
   Chain &c = S.ch;
   c.count = 0; c.pos = 0;
   const double V = S.V;
+  const double iabsV = xinv(fabs(V));                 // loop invariants: same value every step, so hoisting is exact
+  const double isum = xinv(c.csA);
+  double mxD_c = fmax(c.D_l, c.D_r), imxD = xinv(mxD_c);
+  HistCache h;
+  hist_load(h, P, c.hidx);
   while (c.count < maxrec) {
     if (c.status != 0 || !(c.t < S.t_tot) || (A.max_steps > 0 && c.steps >= A.max_steps)) { c.done = 1; break; }
     // ---- dt (find_dt functions.jl:465-490 / C1.jl:93) and update_time! (:1442-1450)
@@ -356,8 +375,9 @@ __device__ inline void chain_build(Scal &S, const KArgs &A, const MemberPtrs &P,
     if (A.dt_mode == DT_ADV) dt = xmul(xdiv(fmin(c.dx1, c.dx2), V), S.CFL);
     else {
       const double mn = fmin(c.dx1, c.dx2), mxD = fmax(c.D_l, c.D_r);
-      double dtV = xmul(mn, xinv(fabs(V)));
-      const double dtD = xmul(xmul(xmul(mn, mn), xinv(mxD)), 50.0);
+      if (mxD != mxD_c) { mxD_c = mxD; imxD = xinv(mxD); }
+      double dtV = xmul(mn, iabsV);
+      const double dtD = xmul(xmul(xmul(mn, mn), imxD), 50.0);
       dtV = xmul(dtV, 0.99);
       if (V == 0.0) dt = xmul(dtD, S.CFL);
       else if (dtV < dtD) dt = xmul(dtV, S.CFL);
@@ -366,8 +386,8 @@ __device__ inline void chain_build(Scal &S, const KArgs &A, const MemberPtrs &P,
     double t = xadd(c.t, dt);
     if (t > S.t_tot) { dt = xsub(dt, xsub(t, S.t_tot)); t = S.t_tot; }
     double KD, Tt, D_l, D_r;
-    int cur = c.hidx;
-    int rc = chain_update_params(S, A, P, t, &cur, &KD, &Tt, &D_l, &D_r);
+    int rc = chain_update_params(S, A, P, t, h, &KD, &Tt, &D_l, &D_r);
+    const int cur = h.i;
     // ---- advect_interface_regrid! (functions.jl:29-64) on scalars
     const double Rnew = xadd(c.Ri1, xmul(V, dt));
     int n1s = c.n1, n2s = c.n2;
@@ -407,7 +427,6 @@ __device__ inline void chain_build(Scal &S, const KArgs &A, const MemberPtrs &P,
     c.D_l = D_l; c.D_r = D_r;
     c.Ri1 = Rnew;
     // ---- closed-form mesh scalars of define_new_grid (:402-410) from the cached scan totals
-    const double isum = xinv(c.csA);
     const double xl_last = xmul(xmul(c.csA, Rnew), isum);      // X_left[nr1-1]
     const double xl_m2 = xmul(xmul(c.csB, Rnew), isum);        // X_left[nr1-2]
     const double d = xsub(xl_last, xl_m2);
@@ -577,24 +596,7 @@ __device__ __forceinline__ void reduced_solve(double *rs, double *rd, double *ru
   const int lane = threadIdx.x;  // caller guarantees threadIdx.x < 32
   const int g0 = lane * RPL;
   double A[RPL], G[RPL], R0[RPL], R1[RPL];
-  // pass 2 (backward over interior rows): first row in terms of the two separators
-  double bA = 0.0, bG = -1.0, bR0 = 0.0, bR1 = 0.0;
-  if (RPL > 1) {
-    int g = g0 + RPL - 2;
-    double inv = frcp_(rd[g]);
-    bA = rs[g] * inv; bG = ru[g] * inv; bR0 = r0[g] * inv; bR1 = r1[g] * inv;
-#pragma unroll
-    for (int k = RPL - 3; k >= 0; --k) {
-      g = g0 + k;
-      const double e = ru[g];
-      inv = frcp_(rd[g] - e * bA);
-      bA = rs[g] * inv;
-      bG = -e * bG * inv;
-      bR0 = (r0[g] - e * bR0) * inv;
-      bR1 = (r1[g] - e * bR1) * inv;
-    }
-  }
-  // pass 1 (forward): every row in terms of previous separator and next row
+  // forward pass: every row of the lane's chunk in terms of the previous separator and the next row
   {
     double inv = frcp_(rd[g0]);
     A[0] = rs[g0] * inv; G[0] = ru[g0] * inv; R0[0] = r0[g0] * inv; R1[0] = r1[g0] * inv;
@@ -607,6 +609,16 @@ __device__ __forceinline__ void reduced_solve(double *rs, double *rd, double *ru
       G[k] = ru[g] * inv;
       R0[k] = (r0[g] - sb * R0[k - 1]) * inv;
       R1[k] = (r1[g] - sb * R1[k - 1]) * inv;
+    }
+  }
+  // division-free backward accumulation: first row of the chunk in terms of the two separators
+  double bA = 0.0, bG = -1.0, bR0 = 0.0, bR1 = 0.0;
+  if (RPL > 1) {
+    bA = A[RPL - 2]; bG = G[RPL - 2]; bR0 = R0[RPL - 2]; bR1 = R1[RPL - 2];
+#pragma unroll
+    for (int k = RPL - 3; k >= 0; --k) {
+      const double Gk = G[k];
+      bR0 = R0[k] - Gk * bR0; bR1 = R1[k] - Gk * bR1; bA = A[k] - Gk * bA; bG = -Gk * bG;
     }
   }
   // level-3 row of this lane (separator = last row of the lane's chunk), normalised to diag 1
