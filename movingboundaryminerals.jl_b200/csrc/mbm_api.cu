@@ -396,33 +396,59 @@ int simple_shard(const mbm_common *c, const mbm_simple_params *p, mbm_simple_io 
 }
 
 // contiguous blocks of ceil(M/G) members per device, one host thread per device
+// contiguous blocks of ceil(M/G) members per device, one host thread (and stream) per block.  With host buffers a
+// device's block is further cut into pieces that run on their own streams, so that the H2D copy of one piece, the
+// kernel of another and the D2H copy of a third overlap (members never communicate: no ordering is needed).
 template <typename F>
 int run_sharded(const mbm_common *c, F shard_fn) {
   const int G = c->n_devices, M = c->n_members;
   if (M == 0) return 0;
   const int per = (M + G - 1) / G;
-  std::vector<int> rcs(G, 0);
-  std::vector<double> ks(G, 0.0);
+  int pieces = 1;
+  const bool host_buffers = !(c->flags & MBM_FLAG_DEVICE_POINTERS) && !g_have_user_stream;
+  if (host_buffers && per >= 2048) pieces = 4;
+  if (const char *e = getenv("MBM_PIECES")) { const int p = atoi(e); if (p >= 1 && p <= 16) pieces = p; }
+  if (!host_buffers) pieces = 1;
+  struct Job { int m0, m1, dev, g; };
+  std::vector<Job> jobs;
+  for (int g = 0; g < G; ++g) {
+    const int m0 = g * per, m1 = (m0 + per < M) ? (m0 + per) : M;
+    if (m0 >= m1) continue;
+    const int dev = c->device_ids ? c->device_ids[g] : g;
+    const int n = m1 - m0, pp = (n + pieces - 1) / pieces;
+    for (int q = 0; q < pieces; ++q) {
+      const int a = m0 + q * pp, b = (a + pp < m1) ? (a + pp) : m1;
+      if (a < b) jobs.push_back({a, b, dev, g});
+    }
+  }
+  const size_t J = jobs.size();
+  std::vector<int> rcs(J, 0);
+  std::vector<double> ks(J, 0.0);
+  std::vector<long long> nl(J, 0);
   int prev_dev = 0;
   cudaGetDevice(&prev_dev);
-  if (G == 1) {
-    rcs[0] = shard_fn(0, M, c->device_ids ? c->device_ids[0] : 0, &ks[0]);
+  if (J == 1) {
+    rcs[0] = shard_fn(jobs[0].m0, jobs[0].m1, jobs[0].dev, &ks[0]);
+    nl[0] = g_last_kernel_launches;
   } else {
     std::vector<std::thread> th;
-    for (int g = 0; g < G; ++g) {
-      const int m0 = g * per, m1 = (m0 + per < M) ? (m0 + per) : M;
-      if (m0 >= m1) continue;
-      const int dev = c->device_ids ? c->device_ids[g] : g;
-      th.emplace_back([&, g, m0, m1, dev]() { rcs[g] = shard_fn(m0, m1, dev, &ks[g]); });
-    }
+    for (size_t j = 0; j < J; ++j)
+      th.emplace_back([&, j]() {
+        rcs[j] = shard_fn(jobs[j].m0, jobs[j].m1, jobs[j].dev, &ks[j]);
+        nl[j] = g_last_kernel_launches;
+      });
     for (auto &t : th) t.join();
   }
   cudaSetDevice(prev_dev);
-  g_last_kernel_seconds = ks[0];
-  g_last_kernel_seconds_any = ks[0];
-  g_last_kernel_launches_any = g_last_kernel_launches ? g_last_kernel_launches : 1;
-  for (int g = 0; g < G; ++g)
-    if (rcs[g]) return rcs[g];
+  double k0 = 0.0;
+  long long l0 = 0;
+  for (size_t j = 0; j < J; ++j)
+    if (jobs[j].g == jobs[0].g) { k0 += ks[j]; l0 += nl[j]; }
+  g_last_kernel_seconds = k0;
+  g_last_kernel_seconds_any = k0;
+  g_last_kernel_launches_any = l0 ? l0 : 1;
+  for (size_t j = 0; j < J; ++j)
+    if (rcs[j]) return rcs[j];
   return 0;
 }
 
