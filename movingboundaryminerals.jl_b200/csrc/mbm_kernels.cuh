@@ -495,48 +495,6 @@ __device__ __forceinline__ double frcp_(double x) {
   r = fma(fma(-x, r, 1.0), r, r);
   return r;
 }
-__device__ __forceinline__ double pchip_slope_fast(const double *x, const double *y, int n, int i) {
-  if (i == 0 || i == n - 1) return pchip_slope(x, y, n, i);
-  const double ihm = frcp_(x[i] - x[i - 1]), ihp = frcp_(x[i + 1] - x[i]);
-  const double mm = (y[i] - y[i - 1]) * ihm, mp = (y[i + 1] - y[i]) * ihp;
-  double d = (ihm * mm + ihp * mp) * frcp_(ihm + ihp);      // weights 2/h: the factor 2 cancels
-  if (mm * mp < 0.0 || mm == 0.0 || mp == 0.0) d = 0.0;
-  const double lim = 3.0 * fmin(fabs(mm), fabs(mp));
-  const double ad = fmin(fabs(d), lim);
-  return (d > 0.0) ? ad : ((d < 0.0) ? -ad : d);
-}
-// pchip evaluation with an interval search that walks from `guess` (count of old nodes below Xj);
-// identical branch/index semantics as pchip_eval_one (functions.jl:809-837)
-__device__ __noinline__ double pchip_eval_walk(const double *x, const double *y, const double *d, int n, double Xj,
-                                                  int guess, int *cout, int *kout, int *branch) {
-  int c = min(max(guess, 0), n);
-  int steps = 0;
-  bool ok = true;
-  while (c < n && x[c] < Xj) { ++c; if (++steps > 16) { ok = false; break; } }
-  if (ok) while (c > 0 && !(x[c - 1] < Xj)) { --c; if (++steps > 16) { ok = false; break; } }
-  if (!ok) {
-    int lo = 0, hi = n;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (x[mid] < Xj) lo = mid + 1; else hi = mid; }
-    c = lo;
-  }
-  *cout = c;
-  if (c < n && x[c] == Xj) { *kout = c; *branch = 0; return y[c]; }
-  if (c == n) { *kout = n - 1; *branch = 1; return y[n - 1]; }
-  if (c == 0) { *kout = 0; *branch = 2; return y[0]; }
-  const int k = c - 1;
-  *kout = k; *branch = 3;
-  const double x1 = x[k], x2 = x[k + 1], y1 = y[k], y2 = y[k + 1], d1 = d[k], d2 = d[k + 1];
-  const double s = Xj - x1, h = x2 - x1;
-  const double ih = frcp_(h), ih2 = ih * ih, ih3 = ih2 * ih;
-  const double s2 = s * s, s3 = s2 * s, h3 = h * h * h, smh = s - h;
-  const double t1 = (3.0 * h * s2 - 2.0 * s3) * ih3 * y2;
-  const double t2 = (h3 - 3.0 * h * s2 + 2.0 * s3) * ih3 * y1;
-  const double t3 = (s2 * smh) * ih2 * d2;
-  const double t4 = (s * (smh * smh)) * ih2 * d1;
-  return t1 + t2 + t3 + t4;
-}
-
-
 __device__ __forceinline__ double slope_interior(double ihm, double ihp, double mm, double mp) {
   // d = (w- m- + w+ m+)/(w- + w+), w = 2/h (the factor 2 cancels); zero on sign change / zero secant; limiter 3*min|m|
   const double d = (ihm * mm + ihp * mp) * frcp_(ihm + ihp);
@@ -696,7 +654,7 @@ __global__ void __launch_bounds__(T) mbm_step_kernel(const KArgs A, const int me
   if (tid == 0) {
     const int ps = A.pstride;
     S.status = A.status[mem];
-    S.warn = A.warn ? 0 : 0;
+    S.warn = 0;
     S.t = A.t[mem]; S.dt = A.dt[mem]; S.it = A.it[mem]; S.steps = 0;
     if (A.only_deferred) {
       if (S.status == -1) { S.status = 0; S.steps = A.steps_done ? A.steps_done[mem] : 0; if (A.warn) S.warn = A.warn[mem]; }

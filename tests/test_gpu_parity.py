@@ -232,3 +232,49 @@ def test_multi_device_sharding(oracle, cuda_lib):
     assert eo.run(oracle, max_steps=80) == 0
     assert eg.run(cuda_lib, max_steps=80, n_devices=2) == 0
     compare(eo, eg)
+
+
+def test_bitwise_determinism(cuda_lib):
+    """three runs of the same ensemble give identical bits (no order-dependent reductions, no races)"""
+    pars = []
+    for V, res in ((-1e-7, [100, 150]), (1e-7, [100, 150]), (-2e-7, [60, 90]), (5e-8, [130, 131])):
+        p = d.pars_MB_growth(); p.update(V_ip=V, res=res); pars.append(p)
+    e0, _ = d.build_couple_ensemble(pars, cuda_lib)
+    runs = []
+    for _ in range(3):
+        e = e0.copy()
+        assert e.run(cuda_lib, max_steps=200, flags=abi.FLAG_MASS_FINAL) == 0
+        runs.append(e)
+    for k in ("x_left", "C_left", "x_right", "C_right", "res", "it", "Ri", "t", "idx_hash", "Mass", "node_steps"):
+        assert np.array_equal(runs[0].arrays[k], runs[1].arrays[k]) and np.array_equal(runs[0].arrays[k], runs[2].arrays[k]), k
+
+
+def test_edge_cases(oracle, cuda_lib):
+    """empty ensemble; members already at t_tot or frozen on entry are left untouched"""
+    p = d.pars_MB_growth(); p.update(res=[60, 90])
+    e, _ = d.build_couple_ensemble([p, p, p], cuda_lib)
+    e.arrays["t"][1] = e.arrays["t_tot"][1]            # finished member
+    e.arrays["status"][2] = 3                          # frozen member
+    before = {k: e.arrays[k].copy() for k in ("x_left", "C_left", "x_right", "C_right", "res", "it")}
+    assert e.run(cuda_lib, max_steps=20) == 0
+    assert list(e.status) == [0, 0, 3] and list(e.it) == [20, 0, 0]
+    for k, v in before.items():
+        assert np.array_equal(v[1:], e.arrays[k][1:]), k
+    # empty ensemble: the call is a no-op
+    import ctypes as C
+    c, pp, io = e.structs()
+    c.n_members = 0
+    assert cuda_lib.mbm_couple_batch(C.byref(c), C.byref(pp), C.byref(io)) == 0
+    # bad arguments are library-level errors, not crashes
+    c.n_members = 3; c.abi_version = 999
+    assert cuda_lib.mbm_couple_batch(C.byref(c), C.byref(pp), C.byref(io)) == -1
+    c.abi_version = abi.ABI_VERSION; c.flags = abi.FLAG_SOLVER_FAITHFUL
+    assert cuda_lib.mbm_couple_batch(C.byref(c), C.byref(pp), C.byref(io)) == -4     # oracle-only mode
+
+
+def test_whole_run_MB_growth(oracle, cuda_lib):
+    """examples/Diff_couple_MB_growth.jl as shipped, whole run (9 352 steps): end-of-run parity and mass error"""
+    eo, eg = run_both([d.pars_MB_growth()], oracle, cuda_lib, 0)
+    compare(eo, eg, tol=5e-10)
+    assert int(eg.it[0]) == 9352 and list(eg.res[0]) == [200, 398]
+    assert abs((eg.Mass[0] - eg.Mass0[0]) / eg.Mass0[0]) < 1e-10
