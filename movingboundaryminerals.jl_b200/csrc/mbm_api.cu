@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "../../include/mbm_b200.h"
-#include "mbm_kernel_v2.cuh"
+#include "mbm_kernel_fixed.cuh"
 
 namespace {
 
@@ -127,6 +127,37 @@ int launch_v2_T(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, 
   }
 }
 
+template <int T, int NDIM>
+int launch_fixed_TN(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
+  auto kern = mbm::mbm_fixed_kernel<T, NDIM>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) return MBM_RC_CUDA;
+  kern<<<count, T, smem_bytes, s>>>(A, member0);
+  return (cudaGetLastError() == cudaSuccess) ? 0 : MBM_RC_CUDA;
+}
+template <int T>
+int launch_fixed_T(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
+  switch (A.ndim) {
+    case 1: return launch_fixed_TN<T, 1>(A, member0, count, smem_bytes, s);
+    case 2: return launch_fixed_TN<T, 2>(A, member0, count, smem_bytes, s);
+    default: return launch_fixed_TN<T, 3>(A, member0, count, smem_bytes, s);
+  }
+}
+// fixed-interface kernel: nine arrays of kF doubles per member (n1 + n2 <= kF)
+void fixed_plan(int capL, int capR, int nmax_hint, int smem_optin, int *Tf, int *kF) {
+  int kf = capL + capR;
+  if (nmax_hint > 0 && nmax_hint + 8 < kf) kf = (nmax_hint + 8) - (nmax_hint % 8);   // host buffers: size by the data
+  if (const char *e = getenv("MBM_KCAP_FIXED")) { const int a = atoi(e); if (a >= 8 && a < kf) kf = a; }
+  int T = 256;
+  if (kf <= 320) T = 64;
+  else if (kf <= 1100) T = 128;
+  const int static_est = (int)sizeof(mbm::Scal) + 8 * T * 8 + 256;
+  int kmax = (smem_optin - static_est) / (9 * 8);
+  kmax -= kmax % 8;
+  if (kf > kmax) kf = kmax;
+  *Tf = T; *kF = kf;
+}
+
 // combined shared-memory capacity (left | free slot | right) of the tuned kernel: as large as the caps need, within
 // two CTAs per SM (four arrays of kS doubles) and one scan tile per thread and phase (9*T nodes per phase)
 void v2_plan(int capL, int capR, int smem_per_sm, int *T2, int *kS) {
@@ -182,13 +213,21 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
     int smem_sm = 0;
     CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
     v2_plan(A.capL, A.capR, smem_sm, &T2, &A.kcapL);
-    A.kcapR = 0;
     if (A.kcapL < 8) use_v2 = false;
   }
   if (couple_pv && !getenv("MBM_NO_CHAIN")) {
     const int Tr = (use_v2 && T2 > T) ? T2 : T;
     A.recs = (double *)st->scratch((size_t)chunk * (size_t)Tr * mbm::REC_N * sizeof(double));
     if (!A.recs) return st->rc ? st->rc : MBM_RC_OOM;
+  }
+  const bool use_fixed = (couple_pv || A.inner_bc == MBM_BC_DIRICHLET_HOLD) && !use_global && !getenv("MBM_NO_FIXED") &&
+                         A.ndim >= 1 && A.ndim <= 3;
+  int Tf = 128;
+  if (use_fixed) fixed_plan(A.capL, A.capR, A.pad3_, maxOptin, &Tf, &A.kcapR);
+  if (use_fixed && !use_v2) {
+    A.steps_done = (long long *)st->scratch((size_t)count * sizeof(long long));
+    if (!A.steps_done) return st->rc ? st->rc : MBM_RC_OOM;
+    CK(cudaMemsetAsync(A.steps_done, 0, (size_t)count * sizeof(long long), s));
   }
   if (use_v2) {
     A.csbuf = (double *)st->scratch((size_t)chunk * (size_t)(9 * T2 + 8) * sizeof(double));
@@ -217,6 +256,18 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
         case 64: rc = launch_v2_T<64>(A2, m0 + off, n, dyn2, s); break;
         case 128: rc = launch_v2_T<128>(A2, m0 + off, n, dyn2, s); break;
         default: rc = launch_v2_T<256>(A2, m0 + off, n, dyn2, s); break;
+      }
+      if (rc) return rc;
+      ++launches;
+      A.only_deferred = 1;
+    }
+    if (use_fixed) {
+      // fixed-interface members (V_ip == 0): resident kernel that keeps the factorisation
+      const size_t dynf = 9 * (size_t)A.kcapR * sizeof(double);
+      switch (Tf) {
+        case 64: rc = launch_fixed_T<64>(A, m0 + off, n, dynf, s); break;
+        case 128: rc = launch_fixed_T<128>(A, m0 + off, n, dynf, s); break;
+        default: rc = launch_fixed_T<256>(A, m0 + off, n, dynf, s); break;
       }
       if (rc) return rc;
       ++launches;
@@ -315,6 +366,11 @@ int couple_shard(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io 
       A.dens_left = st.in(p->dens_left, (size_t)p->nd * p->nd);
       A.dens_right = st.in(p->dens_right, (size_t)p->nd * p->nd);
     }
+  }
+  if (!st.device_ptrs) {                       // largest node count of the shard (sizes the fixed-interface kernel)
+    long long nmax = 0;
+    for (size_t k = 0; k < n; ++k) { const long long v = io->res[2 * (m0 + k)] + io->res[2 * (m0 + k) + 1]; if (v > nmax) nmax = v; }
+    A.pad3_ = (int)nmax;
   }
   A.x_left = st.inout(io->x_left + (size_t)m0 * capL, n * capL);
   A.C_left = st.inout(io->C_left + (size_t)m0 * capL, n * capL);

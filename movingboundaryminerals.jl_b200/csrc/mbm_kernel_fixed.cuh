@@ -1,0 +1,325 @@
+// mbm_kernel_fixed.cuh — resident kernel for couples whose interface does not move (V_ip == 0): BASELINE.json
+// configs[2] (B1-style flux ensembles) and the fixtures B1, B2, Diff_couple_Flux/MB (fixed), Diff_couple_no_interaction.
+//
+// The mesh never changes, so the per-step system matrix (M/dt + K with the interface rows) only changes when dt or the
+// diffusivities change (last clipped step; Arrhenius D(T(t))).  The kernel keeps the *factorisation* of the partitioned
+// elimination resident in shared memory (per row: fill-in A, G, sub*inv and the mass-matrix row pre-multiplied by inv;
+// per chunk: the constants of the reduced system and of the mass-balance functional) and per step only runs
+//   R_l = mli*C_{l-1} + mdi*C_l + mui*C_{l+1} - fs*R_{l-1}      (right-hand side + forward substitution, 4 FMA/row)
+//   backward accumulation of the chunk's first row, reduced solve (warp 0), 2x2 interface condition, back-substitution.
+// A step whose (dt, D_l, D_r) differ from the factorised ones first re-runs the coefficient sweep (same arithmetic as
+// the tuned moving-interface kernel).  Loop body: reference main_codes/Diff_couple_1D_general_Flux.jl:87-130 with
+// Fl_regrid == 0 (functions.jl:58-61), examples/Diff_couple_MB.jl:87-109, Diff_couple_no_interaction.jl:96-124.
+#pragma once
+#include "mbm_kernel_v2.cuh"
+
+namespace mbm {
+
+template <int T, int NDIM>
+__global__ void __launch_bounds__(T) mbm_fixed_kernel(const KArgs A, const int member0) {
+  extern __shared__ double smem[];
+  __shared__ Scal S;
+  __shared__ double redS[T], redD[T], redU[T], red0[T], red1[T];
+  __shared__ double exA[T], exG[T], exR[T];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int mem = member0 + blockIdx.x;
+  if (mem >= A.M) return;
+  const int SZ = A.kcapR;                    // capacity of this kernel's arrays (n1 + n2 <= SZ)
+  double *X = smem, *C = smem + SZ, *FA = smem + 2 * (size_t)SZ, *FG = smem + 3 * (size_t)SZ, *FS = smem + 4 * (size_t)SZ,
+         *ML = smem + 5 * (size_t)SZ, *MD = smem + 6 * (size_t)SZ, *MU = smem + 7 * (size_t)SZ, *TQ = smem + 8 * (size_t)SZ;
+  const int bc = A.inner_bc;
+  const bool mb = (bc == BC_MB);
+  MemberPtrs P;
+  P.t_ar = A.t_ar + (size_t)mem * A.t_stride;
+  P.T_ar = A.T_ar + (size_t)mem * A.T_stride;
+  P.KD_ar = A.KD_ar + (size_t)mem * A.KD_stride;
+
+  // ---------------- load member ----------------
+  if (tid == 0) {
+    S.status = A.status[mem];
+    S.warn = 0;
+    S.t = A.t[mem]; S.dt = A.dt[mem]; S.it = A.it[mem]; S.steps = 0;
+    S.t_tot = A.t_tot[mem]; S.CFL = A.CFL[mem];
+    S.Di0 = A.Di[2 * (size_t)mem]; S.Di1 = A.Di[2 * (size_t)mem + 1];
+    S.D00 = A.D0 ? A.D0[2 * (size_t)mem] : 0.0; S.D01 = A.D0 ? A.D0[2 * (size_t)mem + 1] : 0.0;
+    S.Ea0 = A.Ea ? A.Ea[2 * (size_t)mem] : 0.0; S.Ea1 = A.Ea ? A.Ea[2 * (size_t)mem + 1] : 0.0;
+    S.R = A.R;
+    S.arrhenius = (S.Di0 == -1.0 && S.Di1 == -1.0);
+    S.bc0 = A.BCout[2 * (size_t)mem]; S.bc1 = A.BCout[2 * (size_t)mem + 1];
+    S.node_steps = A.node_steps ? A.node_steps[mem] : 0;
+    S.hidx = 0; S.Fl = 0; S.KD = 0.0; S.T = 0.0; S.D_l = 0.0; S.D_r = 0.0;
+    S.n1 = (int)A.res[2 * (size_t)mem]; S.n2 = (int)A.res[2 * (size_t)mem + 1];
+    S.gap = 0;
+    S.rho1 = A.rho[2 * (size_t)mem]; S.rho2 = A.rho[2 * (size_t)mem + 1];
+    S.V = A.V_ip ? A.V_ip[mem] : 0.0;
+    S.MRefin = A.MRefin[mem];
+    S.Ri1 = A.Ri[2 * (size_t)mem]; S.Ri2 = A.Ri[2 * (size_t)mem + 1];
+    S.Mass0 = A.Mass0 ? A.Mass0[mem] : 0.0;
+    S.newton_R = A.newton_R ? A.newton_R[mem] : 0.0;
+    S.grid_d = 0.0; S.grid_S = 0.0; S.grid_total = 0.0;          // factorised (dt, D_l, D_r); 0 = none yet
+    // this kernel takes members whose interface is fixed; as a later stage it only looks at handed-over members
+    bool mine = A.only_deferred ? (S.status == -1) : (S.status == 0);
+    const bool ok = (S.V == 0.0 || bc == BC_HOLD) && S.n1 >= 3 && S.n2 >= 3 && S.n1 + S.n2 <= SZ;
+    if (mine && !ok) { if (!A.only_deferred) A.status[mem] = -1; mine = false; }
+    if (mine) S.status = 0;
+    S.use_chain = mine ? 1 : 0;
+    if (mine && A.only_deferred && A.steps_done) S.steps = A.steps_done[mem];
+  }
+  __syncthreads();
+  if (!S.use_chain) return;
+  const int n1 = S.n1, n2 = S.n2, N = n1 + n2, rb = n1;
+  {
+    const double *gxl = A.x_left + (size_t)mem * A.capL, *gcl = A.C_left + (size_t)mem * A.capL;
+    const double *gxr = A.x_right + (size_t)mem * A.capR, *gcr = A.C_right + (size_t)mem * A.capR;
+    for (int i = tid; i < n1; i += T) { X[i] = gxl[i]; C[i] = gcl[i]; }
+    for (int i = tid; i < n2; i += T) { X[rb + i] = gxr[i]; C[rb + i] = gcr[i]; }
+    double v[4] = {1e300, -1e300, 1e300, -1e300}, tm[2] = {1e300, -1e300};
+    for (int i = tid; i < A.hist_len; i += T) {
+      const double tt = P.t_ar[i], TT = P.T_ar[i], kd = P.KD_ar[i];
+      tm[0] = fmin(tm[0], tt); tm[1] = fmax(tm[1], tt);
+      v[2] = fmin(v[2], TT); v[3] = fmax(v[3], TT);
+      v[0] = fmin(v[0], kd); v[1] = fmax(v[1], kd);
+    }
+    v[0] = warp_min(v[0]); v[1] = warp_max(v[1]); v[2] = warp_min(v[2]); v[3] = warp_max(v[3]);
+    tm[0] = warp_min(tm[0]); tm[1] = warp_max(tm[1]);
+    if (lane == 0) { redS[wid] = v[0]; redD[wid] = v[1]; redU[wid] = v[2]; red0[wid] = v[3]; red1[wid] = tm[0]; exA[wid] = tm[1]; }
+    __syncthreads();
+    if (tid == 0) {
+      double a0 = 1e300, a1 = -1e300, a2 = 1e300, a3 = -1e300, a4 = 1e300, a5 = -1e300;
+#pragma unroll 1
+      for (int k = 0; k < T / 32; ++k) {
+        a0 = fmin(a0, redS[k]); a1 = fmax(a1, redD[k]); a2 = fmin(a2, redU[k]); a3 = fmax(a3, red0[k]);
+        a4 = fmin(a4, red1[k]); a5 = fmax(a5, exA[k]);
+      }
+      S.KDmin = a0; S.KDmax = a1; S.Tmin = a2; S.Tmax = a3; S.tmin = a4; S.tmax = a5;
+      S.dx1 = xsub(X[n1 - 1], X[n1 - 2]);                                   // create_grid!, functions.jl:366-367
+      S.dx2 = xsub(X[rb + 1], X[rb]);
+      const int rc = update_t_dependent(S, A, P, false);                   // pre-loop call (e.g. B1.jl:72)
+      if (rc) S.status = rc;
+    }
+  }
+  __syncthreads();
+
+  // ---- partition (fixed for the whole call): block L = rows 0..n1-2 (towards the interface), block R = rows N-1..n1+1
+  const int nbL = n1 - 1, nbR = n2 - 1;
+  int m = (nbL + nbR + T - 1) / T;
+  int KL = (nbL + m - 1) / m, KR = (nbR + m - 1) / m;
+  while (KL + KR > T) { ++m; KL = (nbL + m - 1) / m; KR = (nbR + m - 1) / m; }
+  if (!(m & 1)) { m += 1; KL = (nbL + m - 1) / m; KR = (nbR + m - 1) / m; }
+  const bool active = tid < KL + KR;
+  const int blk = (tid < KL) ? 0 : 1;
+  const int jc = blk ? (tid - KL) : tid;
+  const int nb = blk ? nbR : nbL;
+  const int f = jc * m;
+  const int len = active ? (min(f + m, nb) - f) : 0;
+  const int sdir = blk ? -1 : 1;
+  const int s0 = blk ? (N - 1 - f) : f;
+  const bool lastChunk = active && (jc == (blk ? KR : KL) - 1);
+  const bool dir0 = blk ? (S.bc1 == 1) : (S.bc0 == 1);
+  // per-chunk constants of the factorisation (registers)
+  double cQa = 0.0, cQc = 0.0, cGp = 0.0, cAp = 0.0, cbA = 0.0, cbG = -1.0;
+  double r_s = 0.0, r_u = 0.0, r_inv = 1.0, r_Gp = 0.0;     // reduced row: sub, sup, 1/diag, G of the chunk's last row
+
+  while (true) {
+    if (S.status != 0 || !(S.t < S.t_tot) || (A.max_steps > 0 && S.steps >= A.max_steps)) break;
+    __syncthreads();
+    if (tid == 0) {
+      step_scalars(S, A, P, mem, X, C);                     // dt, time, KD(t), T(t), D(T); V == 0: no advection
+      S.rec_status = (S.dt != S.grid_d || S.D_l != S.grid_S || S.D_r != S.grid_total) ? 1 : 0;   // refactor?
+      if (S.rec_status) { S.grid_d = S.dt; S.grid_S = S.D_l; S.grid_total = S.D_r; }
+    }
+    __syncthreads();
+    if (S.status != 0) break;
+
+    if (S.rec_status) {
+      // ---------------- coefficient sweep: factorise the step matrix (fill_matrix!, functions.jl:510-549) -------------
+      const double idt = frcp(S.dt);
+      const double Dph = blk ? S.D_r : S.D_l;
+      if (active) {
+        double x_self = X[s0], x_prev = 0.0;
+        double pAc = 0.0, pAnext = 0.0, pkk = 0.0;
+        const bool haveP0 = f > 0;
+        if (haveP0) {
+          x_prev = X[s0 - sdir];
+          double A11, A12, A22, kk;
+          if (sdir > 0) elem_mats_fast<NDIM>(x_prev, x_self, Dph, idt, A11, A12, A22, kk);
+          else elem_mats_fast<NDIM>(x_self, x_prev, Dph, idt, A11, A12, A22, kk);
+          pAnext = (sdir > 0) ? A22 : A11; pAc = A12; pkk = kk;
+        }
+        double Ap = 0.0, Gp = 0.0, Qb = 0.0, Qa = 0.0, Qc = 0.0;
+        double Vs = 0.0, Vm = 0.0;
+        if (mb) { Vs = powd<NDIM>(x_self); Vm = haveP0 ? powd<NDIM>(x_prev) : Vs; }
+        int s = s0;
+#pragma unroll 1
+        for (int k = 0; k < len; ++k, s += sdir) {
+          const double x_next = X[s + sdir];
+          double A11, A12, A22, kk;
+          if (sdir > 0) elem_mats_fast<NDIM>(x_self, x_next, Dph, idt, A11, A12, A22, kk);
+          else elem_mats_fast<NDIM>(x_next, x_self, Dph, idt, A11, A12, A22, kk);
+          const double nAself = (sdir > 0) ? A11 : A22, nAnext = (sdir > 0) ? A22 : A11;
+          double diag = (nAself - kk) + (pAnext - pkk);
+          double ml = pAc, md = nAself + pAnext, mu = A12;            // mass-matrix row / dt: rhs = ml*C- + md*C + mu*C+
+          double sup = A12 + kk, sub = pAc + pkk;
+          if (dir0 && f + k == 0) { diag = 1.0; sup = 0.0; sub = 0.0; ml = 0.0; md = 1.0; mu = 0.0; }   // set_outer_bc!
+          const double inv = frcp(diag - sub * Gp);
+          const double An = (k == 0) ? (sub * inv) : (-sub * Ap * inv);
+          const double Gn = sup * inv;
+          FA[s] = An; FG[s] = Gn; FS[s] = sub * inv; ML[s] = ml * inv; MD[s] = md * inv; MU[s] = mu * inv;
+          if (mb) {
+            const double Vn = powd<NDIM>(x_next);
+            const double wgt = 0.5 * fabs(Vn - Vs) + 0.5 * fabs(Vs - Vm);
+            if (k < len - 1) { const double tq = Qb + wgt; TQ[s] = tq; Qa = fma(-tq, An, Qa); Qb = -tq * Gn; }
+            else { Qc = Qb + wgt; TQ[s] = 0.0; }
+            Vm = Vs; Vs = Vn;
+          }
+          Ap = An; Gp = Gn;
+          x_prev = x_self; x_self = x_next; pAc = A12; pAnext = nAnext; pkk = kk;
+        }
+        cQa = Qa; cQc = Qc; cGp = Gp; cAp = Ap;
+        // backward accumulation of the matrix part (bA, bG): first row of the chunk in terms of the two separators
+        cbA = 0.0; cbG = -1.0;
+        if (len > 1) {
+          int sb = s0 + sdir * (len - 2);
+          cbA = FA[sb]; cbG = FG[sb];
+#pragma unroll 1
+          for (int k = len - 3; k >= 0; --k) { sb -= sdir; const double Gk = FG[sb]; cbA = FA[sb] - Gk * cbA; cbG = -Gk * cbG; }
+        }
+        exA[tid] = cbA; exG[tid] = cbG;
+      }
+      __syncthreads();
+      if (active) {
+        if (!lastChunk) {
+          const double nA = exA[tid + 1], nG = exG[tid + 1];
+          r_inv = frcp(1.0 - cGp * nA); r_s = cAp * r_inv; r_u = -cGp * nG * r_inv;
+        } else { r_inv = 1.0; r_s = cAp; r_u = 0.0; }
+        r_Gp = cGp;
+      }
+    }
+
+    // ---------------- right-hand side + forward substitution with the resident factors ----------------------------------
+    const int p = n1 - 1, q = rb;
+    const double a_old = C[p], b_old = C[q];
+    double c_halo_prev = 0.0, c_halo_next = 0.0;
+    if (active) {
+      if (f > 0) c_halo_prev = C[s0 - sdir];
+      c_halo_next = C[s0 + sdir * len];
+    }
+    __syncthreads();
+    double P0 = 0.0, Rp = 0.0, bR = 0.0;
+    if (active) {
+      double c_prev = c_halo_prev, c_self = C[s0];
+      int s = s0;
+#pragma unroll 2
+      for (int k = 0; k < len; ++k, s += sdir) {
+        const double c_next = (k == len - 1) ? c_halo_next : C[s + sdir];
+        const double Rn = fma(ML[s], c_prev, fma(MD[s], c_self, fma(MU[s], c_next, -FS[s] * Rp)));
+        C[s] = Rn;
+        if (mb) P0 = fma(TQ[s], Rn, P0);
+        Rp = Rn; c_prev = c_self; c_self = c_next;
+      }
+      if (len > 1) {
+        int sb = s0 + sdir * (len - 2);
+        bR = C[sb];
+#pragma unroll 1
+        for (int k = len - 3; k >= 0; --k) { sb -= sdir; bR = C[sb] - FG[sb] * bR; }
+      }
+      exR[tid] = bR;
+    }
+    __syncthreads();
+    if (active) {
+      if (!lastChunk) { redS[tid] = r_s; redD[tid] = 1.0; redU[tid] = r_u; red0[tid] = (Rp - r_Gp * exR[tid + 1]) * r_inv; red1[tid] = 0.0; }
+      else { redS[tid] = r_s; redD[tid] = 1.0; redU[tid] = 0.0; red0[tid] = Rp; red1[tid] = -r_Gp; }
+    } else { redS[tid] = 0.0; redD[tid] = 1.0; redU[tid] = 0.0; red0[tid] = 0.0; red1[tid] = 0.0; }
+    __syncthreads();
+    if (tid < 32) reduced_solve<T>(redS, redD, redU, red0, red1);
+    __syncthreads();
+
+    // ---------------- interface condition (set_inner_bc_flux! / _mb! / Dirichlet hold) ----------------------------------
+    double aif, bif;
+    if (bc == BC_FLUX) {
+      const double idxl = frcp(X[p] - X[p - 1]), idxr = frcp(X[q + 1] - X[q]);
+      const double al = -S.rho1 * S.D_l * idxl, be = S.V * S.rho1 + S.rho1 * S.D_l * idxl;
+      const double ga = -S.V * S.rho2 + S.rho2 * S.D_r * idxr, de = -S.rho2 * S.D_r * idxr;
+      const double U0 = red0[KL - 1], U1 = red1[KL - 1], W0 = red0[KL + KR - 1], W1 = red1[KL + KR - 1];
+      const double ca = be + al * U1, cb = ga + de * W1;
+      bif = -(al * U0 + de * W0) / (ca * S.KD + cb);
+      aif = S.KD * bif;
+    } else if (mb) {
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+      if (active) {
+        const double s0v = red0[tid], s1v = red1[tid];
+        const double q0 = (jc > 0) ? red0[tid - 1] : 0.0, q1 = (jc > 0) ? red1[tid - 1] : 0.0;
+        const double c0 = P0 + cQa * q0 + cQc * s0v, c1 = cQa * q1 + cQc * s1v;
+        if (blk == 0) { v[0] = c0; v[1] = c1; } else { v[2] = c0; v[3] = c1; }
+      }
+      block_sum4<T>(v, S.red);
+      const double Vp_ = powd<NDIM>(X[p]), Vq_ = powd<NDIM>(X[q]);
+      const double wp = 0.5 * (Vq_ - Vp_) + 0.5 * (Vp_ - powd<NDIM>(X[p - 1]));
+      const double wq = 0.5 * (powd<NDIM>(X[q + 1]) - Vq_) + 0.5 * (Vq_ - Vp_);
+      bif = (S.Mass0 - (v[0] + v[2])) / ((v[1] + wp) * S.KD + (v[3] + wq));
+      aif = S.KD * bif;
+    } else { aif = a_old; bif = b_old; }
+    // ---------------- back-substitution -----------------------------------------------------------------------------------
+    if (active) {
+      const double beta = blk ? bif : aif;
+      const double sj = red0[tid] + red1[tid] * beta;
+      const double sp = (jc > 0) ? (red0[tid - 1] + red1[tid - 1] * beta) : 0.0;
+      double cn = sj;
+      int sb = s0 + sdir * (len - 1);
+      C[sb] = cn;
+#pragma unroll 2
+      for (int k = len - 2; k >= 0; --k) { sb -= sdir; cn = C[sb] - FA[sb] * sp - FG[sb] * cn; C[sb] = cn; }
+    }
+    if (tid == 0) {
+      C[p] = aif; C[q] = bif;
+      S.steps += 1;
+    }
+    __syncthreads();
+    if (tid == 0 && (!isfinite(C[0]) || !isfinite(C[N - 1]) || !isfinite(C[p]))) S.status = 11;
+    if ((A.flags & F_RECORD) && A.rec) {
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int i = tid; i < n1 - 1; i += T)
+        v[0] += 0.5 * (S.rho1 * powd<NDIM>(X[i + 1]) - S.rho1 * powd<NDIM>(X[i])) * (C[i] + C[i + 1]);
+      for (int i = tid; i < n2 - 1; i += T)
+        v[1] += 0.5 * (S.rho2 * powd<NDIM>(X[rb + i + 1]) - S.rho2 * powd<NDIM>(X[rb + i])) * (C[rb + i] + C[rb + i + 1]);
+      block_sum4<T>(v, S.red);
+      if (tid == 0 && S.it >= 1 && S.it - 1 < A.rec_cap) {
+        double *r = A.rec + ((size_t)mem * (size_t)A.rec_cap + (size_t)(S.it - 1)) * 4;
+        r[0] = v[0] + v[1]; r[1] = S.T; r[2] = S.KD; r[3] = S.Ri1;
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  // ---------------- store member ----------------
+  {
+    double *gcl = A.C_left + (size_t)mem * A.capL, *gcr = A.C_right + (size_t)mem * A.capR;
+    for (int i = tid; i < n1; i += T) gcl[i] = C[i];
+    for (int i = tid; i < n2; i += T) gcr[i] = C[rb + i];
+    if ((A.flags & F_MASS_FINAL) && A.Mass) {
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int i = tid; i < n1 - 1; i += T)
+        v[0] += 0.5 * (S.rho1 * powd<NDIM>(X[i + 1]) - S.rho1 * powd<NDIM>(X[i])) * (C[i] + C[i + 1]);
+      for (int i = tid; i < n2 - 1; i += T)
+        v[1] += 0.5 * (S.rho2 * powd<NDIM>(X[rb + i + 1]) - S.rho2 * powd<NDIM>(X[rb + i])) * (C[rb + i] + C[rb + i + 1]);
+      block_sum4<T>(v, S.red);
+      if (tid == 0) A.Mass[mem] = v[0] + v[1];
+    }
+    if (tid == 0) {
+      A.status[mem] = S.status;
+      if (A.steps_done) A.steps_done[mem] = S.steps;
+      if (A.warn) A.warn[mem] = S.warn;
+      A.t[mem] = S.t; A.dt[mem] = S.dt; A.it[mem] = S.it;
+      if (A.dx1) A.dx1[mem] = S.dx1;
+      if (A.dx2) A.dx2[mem] = S.dx2;
+      if (A.last) {
+        double *L = A.last + 8 * (size_t)mem;
+        L[0] = S.D_l; L[1] = S.D_r; L[2] = S.KD; L[3] = S.T; L[4] = S.V; L[5] = S.rho1; L[6] = S.rho2; L[7] = 0.0;
+      }
+      if (A.node_steps) A.node_steps[mem] = S.node_steps;
+    }
+  }
+}
+
+}  // namespace mbm
