@@ -16,11 +16,12 @@
 namespace mbm {
 
 template <int T, int NDIM>
-__global__ void __launch_bounds__(T) mbm_fixed_kernel(const KArgs A, const int member0) {
+__global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, const int member0) {
   extern __shared__ double smem[];
   __shared__ Scal S;
   __shared__ double redS[T], redD[T], redU[T], red0[T], red1[T];
   __shared__ double exA[T], exG[T], exR[T];
+  __shared__ double red1c[T];                // solution of the reduced system for the interface-unknown column (matrix-only)
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int mem = member0 + blockIdx.x;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(T) mbm_fixed_kernel(const KArgs A, const int m
     S.grid_d = 0.0; S.grid_S = 0.0; S.grid_total = 0.0;          // factorised (dt, D_l, D_r); 0 = none yet
     // this kernel takes members whose interface is fixed; as a later stage it only looks at handed-over members
     bool mine = A.only_deferred ? (S.status == -1) : (S.status == 0);
-    const bool ok = (S.V == 0.0 || bc == BC_HOLD) && S.n1 >= 3 && S.n2 >= 3 && S.n1 + S.n2 <= SZ;
+    const bool ok = (S.V == 0.0) && S.n1 >= 3 && S.n2 >= 3 && S.n1 + S.n2 <= SZ;
     if (mine && !ok) { if (!A.only_deferred) A.status[mem] = -1; mine = false; }
     if (mine) S.status = 0;
     S.use_chain = mine ? 1 : 0;
@@ -120,14 +121,34 @@ __global__ void __launch_bounds__(T) mbm_fixed_kernel(const KArgs A, const int m
   // per-chunk constants of the factorisation (registers)
   double cQa = 0.0, cQc = 0.0, cGp = 0.0, cAp = 0.0, cbA = 0.0, cbG = -1.0;
   double r_s = 0.0, r_u = 0.0, r_inv = 1.0, r_Gp = 0.0;     // reduced row: sub, sup, 1/diag, G of the chunk's last row
+  double dt_full = 0.0, dtD_l = -1.0, dtD_r = -1.0;         // thread 0: cached find_dt
+  HistCache hc;
+  if (tid == 0) hist_load(hc, P, S.hidx);
 
   while (true) {
     if (S.status != 0 || !(S.t < S.t_tot) || (A.max_steps > 0 && S.steps >= A.max_steps)) break;
     __syncthreads();
     if (tid == 0) {
-      step_scalars(S, A, P, mem, X, C);                     // dt, time, KD(t), T(t), D(T); V == 0: no advection
-      S.rec_status = (S.dt != S.grid_d || S.D_l != S.grid_S || S.D_r != S.grid_total) ? 1 : 0;   // refactor?
-      if (S.rec_status) { S.grid_d = S.dt; S.grid_S = S.D_l; S.grid_total = S.D_r; }
+      // scalar phase (V_ip == 0: no advection).  find_dt (functions.jl:465-490) only changes with D; KD(t), T(t) by
+      // linear_interpolation_1D with a cached interval (same arithmetic as update_t_dependent_param!, :1350-1378)
+      if (!(S.D_l == dtD_l && S.D_r == dtD_r)) {
+        const double mn = fmin(S.dx1, S.dx2), mxD = fmax(S.D_l, S.D_r);
+        dt_full = xmul(xmul(xmul(xmul(mn, mn), xinv(mxD)), 50.0), S.CFL);
+        dtD_l = S.D_l; dtD_r = S.D_r;
+      }
+      S.dt = dt_full;
+      S.t = xadd(S.t, S.dt);
+      S.it += 1;
+      if (S.t > S.t_tot) { S.dt = xsub(S.dt, xsub(S.t, S.t_tot)); S.t = S.t_tot; }
+      double KD, Tt, Dl, Dr;
+      const int rc = chain_update_params(S, A, P, S.t, hc, &KD, &Tt, &Dl, &Dr);
+      if (rc) S.status = rc;
+      else {
+        S.KD = KD; S.T = Tt; S.D_l = Dl; S.D_r = Dr;
+        S.node_steps += N;
+        S.rec_status = (S.dt != S.grid_d || S.D_l != S.grid_S || S.D_r != S.grid_total) ? 1 : 0;   // refactor?
+        if (S.rec_status) { S.grid_d = S.dt; S.grid_S = S.D_l; S.grid_total = S.D_r; }
+      }
     }
     __syncthreads();
     if (S.status != 0) break;
@@ -195,6 +216,13 @@ __global__ void __launch_bounds__(T) mbm_fixed_kernel(const KArgs A, const int m
         } else { r_inv = 1.0; r_s = cAp; r_u = 0.0; }
         r_Gp = cGp;
       }
+      // the interface-unknown column of the reduced system depends on the matrix only: solve it once per factorisation
+      if (active) { redS[tid] = r_s; redD[tid] = 1.0; redU[tid] = lastChunk ? 0.0 : r_u; red0[tid] = 0.0; red1[tid] = lastChunk ? -r_Gp : 0.0; }
+      else { redS[tid] = 0.0; redD[tid] = 1.0; redU[tid] = 0.0; red0[tid] = 0.0; red1[tid] = 0.0; }
+      __syncthreads();
+      if (tid < 32) reduced_solve<T, 2>(redS, redD, redU, red0, red1);
+      __syncthreads();
+      red1c[tid] = red1[tid];
     }
 
     // ---------------- right-hand side + forward substitution with the resident factors ----------------------------------
@@ -228,11 +256,11 @@ __global__ void __launch_bounds__(T) mbm_fixed_kernel(const KArgs A, const int m
     }
     __syncthreads();
     if (active) {
-      if (!lastChunk) { redS[tid] = r_s; redD[tid] = 1.0; redU[tid] = r_u; red0[tid] = (Rp - r_Gp * exR[tid + 1]) * r_inv; red1[tid] = 0.0; }
-      else { redS[tid] = r_s; redD[tid] = 1.0; redU[tid] = 0.0; red0[tid] = Rp; red1[tid] = -r_Gp; }
-    } else { redS[tid] = 0.0; redD[tid] = 1.0; redU[tid] = 0.0; red0[tid] = 0.0; red1[tid] = 0.0; }
+      if (!lastChunk) { redS[tid] = r_s; redD[tid] = 1.0; redU[tid] = r_u; red0[tid] = (Rp - r_Gp * exR[tid + 1]) * r_inv; }
+      else { redS[tid] = r_s; redD[tid] = 1.0; redU[tid] = 0.0; red0[tid] = Rp; }
+    } else { redS[tid] = 0.0; redD[tid] = 1.0; redU[tid] = 0.0; red0[tid] = 0.0; }
     __syncthreads();
-    if (tid < 32) reduced_solve<T>(redS, redD, redU, red0, red1);
+    if (tid < 32) reduced_solve<T, 1>(redS, redD, redU, red0, red1);
     __syncthreads();
 
     // ---------------- interface condition (set_inner_bc_flux! / _mb! / Dirichlet hold) ----------------------------------
@@ -241,15 +269,15 @@ __global__ void __launch_bounds__(T) mbm_fixed_kernel(const KArgs A, const int m
       const double idxl = frcp(X[p] - X[p - 1]), idxr = frcp(X[q + 1] - X[q]);
       const double al = -S.rho1 * S.D_l * idxl, be = S.V * S.rho1 + S.rho1 * S.D_l * idxl;
       const double ga = -S.V * S.rho2 + S.rho2 * S.D_r * idxr, de = -S.rho2 * S.D_r * idxr;
-      const double U0 = red0[KL - 1], U1 = red1[KL - 1], W0 = red0[KL + KR - 1], W1 = red1[KL + KR - 1];
+      const double U0 = red0[KL - 1], U1 = red1c[KL - 1], W0 = red0[KL + KR - 1], W1 = red1c[KL + KR - 1];
       const double ca = be + al * U1, cb = ga + de * W1;
       bif = -(al * U0 + de * W0) / (ca * S.KD + cb);
       aif = S.KD * bif;
     } else if (mb) {
       double v[4] = {0.0, 0.0, 0.0, 0.0};
       if (active) {
-        const double s0v = red0[tid], s1v = red1[tid];
-        const double q0 = (jc > 0) ? red0[tid - 1] : 0.0, q1 = (jc > 0) ? red1[tid - 1] : 0.0;
+        const double s0v = red0[tid], s1v = red1c[tid];
+        const double q0 = (jc > 0) ? red0[tid - 1] : 0.0, q1 = (jc > 0) ? red1c[tid - 1] : 0.0;
         const double c0 = P0 + cQa * q0 + cQc * s0v, c1 = cQa * q1 + cQc * s1v;
         if (blk == 0) { v[0] = c0; v[1] = c1; } else { v[2] = c0; v[3] = c1; }
       }
@@ -263,8 +291,8 @@ __global__ void __launch_bounds__(T) mbm_fixed_kernel(const KArgs A, const int m
     // ---------------- back-substitution -----------------------------------------------------------------------------------
     if (active) {
       const double beta = blk ? bif : aif;
-      const double sj = red0[tid] + red1[tid] * beta;
-      const double sp = (jc > 0) ? (red0[tid - 1] + red1[tid - 1] * beta) : 0.0;
+      const double sj = red0[tid] + red1c[tid] * beta;
+      const double sp = (jc > 0) ? (red0[tid - 1] + red1c[tid - 1] * beta) : 0.0;
       double cn = sj;
       int sb = s0 + sdir * (len - 1);
       C[sb] = cn;

@@ -548,7 +548,7 @@ __device__ __forceinline__ double pchip_eval_otf(const double *x, const double *
 
 // ---- reduced-system solve (levels 2 and 3): warp 0 solves the T-row tridiagonal system with two right-
 // hand sides held in shared memory (rs: sub, rd: diag, ru: sup, r0, r1); solution overwrites r0, r1.
-template <int T>
+template <int T, int NRHS = 2>
 __device__ __forceinline__ void reduced_solve(double *rs, double *rd, double *ru, double *r0, double *r1) {
   constexpr int RPL = T / 32;
   const int lane = threadIdx.x;  // caller guarantees threadIdx.x < 32
@@ -557,7 +557,7 @@ __device__ __forceinline__ void reduced_solve(double *rs, double *rd, double *ru
   // forward pass: every row of the lane's chunk in terms of the previous separator and the next row
   {
     double inv = frcp_(rd[g0]);
-    A[0] = rs[g0] * inv; G[0] = ru[g0] * inv; R0[0] = r0[g0] * inv; R1[0] = r1[g0] * inv;
+    A[0] = rs[g0] * inv; G[0] = ru[g0] * inv; R0[0] = r0[g0] * inv; R1[0] = (NRHS > 1) ? r1[g0] * inv : 0.0;
 #pragma unroll
     for (int k = 1; k < RPL; ++k) {
       const int g = g0 + k;
@@ -566,7 +566,7 @@ __device__ __forceinline__ void reduced_solve(double *rs, double *rd, double *ru
       A[k] = -sb * A[k - 1] * inv;
       G[k] = ru[g] * inv;
       R0[k] = (r0[g] - sb * R0[k - 1]) * inv;
-      R1[k] = (r1[g] - sb * R1[k - 1]) * inv;
+      R1[k] = (NRHS > 1) ? (r1[g] - sb * R1[k - 1]) * inv : 0.0;
     }
   }
   // division-free backward accumulation: first row of the chunk in terms of the two separators
@@ -615,12 +615,12 @@ __device__ __forceinline__ void reduced_solve(double *rs, double *rd, double *ru
   double sp0 = __shfl_up_sync(0xffffffffu, p0, 1), sp1 = __shfl_up_sync(0xffffffffu, p1, 1);
   if (lane == 0) { sp0 = 0.0; sp1 = 0.0; }
   double c0 = p0, c1 = p1;
-  r0[g0 + RPL - 1] = c0; r1[g0 + RPL - 1] = c1;
+  r0[g0 + RPL - 1] = c0; if (NRHS > 1) r1[g0 + RPL - 1] = c1;
 #pragma unroll
   for (int k = RPL - 2; k >= 0; --k) {
     c0 = R0[k] - A[k] * sp0 - G[k] * c0;
     c1 = R1[k] - A[k] * sp1 - G[k] * c1;
-    r0[g0 + k] = c0; r1[g0 + k] = c1;
+    r0[g0 + k] = c0; if (NRHS > 1) r1[g0 + k] = c1;
   }
 }
 
