@@ -3,6 +3,7 @@
 every ensemble against the CPU oracle.  These are parity-test cases, not bench lines (bench.py measures c4);
 the numbers go to profiles/ as a record of where each kernel variant stands."""
 import json
+import os
 import sys
 import time
 from pathlib import Path
@@ -10,6 +11,7 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
+os.environ.setdefault("MBM_PIECES", "1")     # one stream: kernel_s is then the plain sum of the kernel launches
 sys.path.insert(0, str(ROOT))
 import mbm_b200  # noqa: E402
 from mbm_b200 import abi, drivers as d, ensembles as E  # noqa: E402
