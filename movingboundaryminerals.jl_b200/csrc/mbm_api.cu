@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "../../include/mbm_b200.h"
-#include "mbm_kernel_fixed.cuh"
+#include "mbm_kernel_stream.cuh"
 
 namespace {
 
@@ -143,6 +143,19 @@ int launch_fixed_T(const mbm::KArgs &A, int member0, int count, size_t smem_byte
     default: return launch_fixed_TN<T, 3>(A, member0, count, smem_bytes, s);
   }
 }
+template <int NDIM>
+int launch_stream_N(const mbm::KArgs &A, int member0, int count, cudaStream_t s) {
+  mbm::mbm_stream_kernel<256, NDIM><<<count, 256, 0, s>>>(A, member0);
+  return (cudaGetLastError() == cudaSuccess) ? 0 : MBM_RC_CUDA;
+}
+int launch_stream(const mbm::KArgs &A, int member0, int count, cudaStream_t s) {
+  switch (A.ndim) {
+    case 1: return launch_stream_N<1>(A, member0, count, s);
+    case 2: return launch_stream_N<2>(A, member0, count, s);
+    default: return launch_stream_N<3>(A, member0, count, s);
+  }
+}
+
 // fixed-interface kernel: nine arrays of kF doubles per member (n1 + n2 <= kF)
 void fixed_plan(int capL, int capR, int nmax_hint, int smem_optin, int *Tf, int *kF) {
   int kf = capL + capR;
@@ -205,6 +218,16 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
     A.workspace = (double *)st->scratch((size_t)chunk * per_cta * sizeof(double));
     if (!A.workspace) return st->rc ? st->rc : MBM_RC_OOM;
   }
+  // streaming kernel (long profiles on uniform meshes): chunk-interleaved workspace of 6 arrays x MC rows x 256 columns
+  const bool use_stream = use_global && (A.inner_bc == MBM_BC_FLUX || A.inner_bc == MBM_BC_MB) && !getenv("MBM_NO_STREAM") &&
+                          A.ndim >= 1 && A.ndim <= 3;
+  mbm::KArgs AS = A;
+  if (use_stream) {
+    const int MC = (A.capL + A.capR + 2 + 253) / 254 + 1;
+    AS.kcapL = MC;
+    AS.workspace = (double *)st->scratch((size_t)chunk * 6 * (size_t)MC * 256 * sizeof(double));
+    if (!AS.workspace) return st->rc ? st->rc : MBM_RC_OOM;
+  }
   A.use_global = use_global ? 1 : 0;
   const bool couple_pv = (A.inner_bc == MBM_BC_FLUX || A.inner_bc == MBM_BC_MB);
   bool use_v2 = couple_pv && !use_global && !getenv("MBM_NO_CHAIN") && !getenv("MBM_NO_V2") && A.ndim >= 1 && A.ndim <= 3;
@@ -224,7 +247,7 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
                          A.ndim >= 1 && A.ndim <= 3;
   int Tf = 128;
   if (use_fixed) fixed_plan(A.capL, A.capR, A.pad3_, maxOptin, &Tf, &A.kcapR);
-  if (use_fixed && !use_v2) {
+  if ((use_fixed || use_stream) && !use_v2) {
     A.steps_done = (long long *)st->scratch((size_t)count * sizeof(long long));
     if (!A.steps_done) return st->rc ? st->rc : MBM_RC_OOM;
     CK(cudaMemsetAsync(A.steps_done, 0, (size_t)count * sizeof(long long), s));
@@ -269,6 +292,13 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
         case 128: rc = launch_fixed_T<128>(A, m0 + off, n, dynf, s); break;
         default: rc = launch_fixed_T<256>(A, m0 + off, n, dynf, s); break;
       }
+      if (rc) return rc;
+      ++launches;
+      A.only_deferred = 1;
+    }
+    if (use_stream) {
+      AS.steps_done = A.steps_done; AS.only_deferred = A.only_deferred; AS.recs = A.recs;
+      rc = launch_stream(AS, m0 + off, n, s);
       if (rc) return rc;
       ++launches;
       A.only_deferred = 1;

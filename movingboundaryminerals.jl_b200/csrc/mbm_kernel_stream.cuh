@@ -1,0 +1,493 @@
+// mbm_kernel_stream.cuh — global-memory ("streaming") kernel for long profiles: BASELINE.json configs[4]
+// (n = 65,536 nodes per phase, MRefin = 1: the only mesh the reference can generate at that size).
+// Covers prescribed-velocity couples (flux / mb, V_ip != 0) on uniform meshes; everything else that does not fit
+// shared memory still runs in the general kernel on a node-major global workspace.
+//
+// One CTA per member, but the member's arrays live in global memory in a CHUNK-INTERLEAVED layout: thread t owns
+// column t (m consecutive nodes of one phase, ordered towards the interface) and element k of column t is stored at
+// k*T + t, so that every sweep of the solve and of the regrid reads and writes fully coalesced 8-byte streams:
+//   forward sweep   read x, C           write A, G, R (R in place of C)
+//   backward accumulation / back-substitution   read A, G, R   write C
+//   regrid          read x, C (walking window)   write x_new, C_new (in the next step's layout)
+// Both phases look the same in this layout: the left phase is stored by node index, the right phase by REVERSED node
+// index, so "towards the interface" is "k increasing" for both and the node the interface advection inserts
+// (functions.jl:33-35 / :46-48) is an append in either case.  The roofline that bounds this kernel is HBM:
+// algorithmic 32 B per node-step; this implementation moves ~128 B per node-step.
+#pragma once
+#include "mbm_kernel_fixed.cuh"
+
+namespace mbm {
+
+struct StreamLayout {
+  int m;        // nodes per column
+  int colR0;    // first column of the right phase
+};
+__device__ __forceinline__ size_t saddr(int T, int col, int k) { return (size_t)k * T + col; }
+// phase-ordered index (left: node index; right: reversed node index) -> address
+__device__ __forceinline__ size_t paddr(int T, const StreamLayout &L, int phase, int idx) {
+  const int col = (phase ? L.colR0 : 0) + idx / L.m;
+  return (size_t)(idx % L.m) * T + col;
+}
+
+// pchip slope at phase-ordered index i of a phase with n nodes stored in layout L (functions.jl:786-806).  The slope
+// formulas are symmetric under reversal of the node order except for the sign of the secants, which cancels.
+template <int T>
+__device__ __forceinline__ double stream_slope(const double *X, const double *C, const StreamLayout &L, int phase, int n,
+                                               int i) {
+  if (i == 0 || i == n - 1) {
+    const int a = (i == 0) ? 0 : n - 1, b = (i == 0) ? 1 : n - 2, c = (i == 0) ? 2 : n - 3;
+    const double xa = X[paddr(T, L, phase, a)], xb = X[paddr(T, L, phase, b)], xc = X[paddr(T, L, phase, c)];
+    const double ya = C[paddr(T, L, phase, a)], yb = C[paddr(T, L, phase, b)], yc = C[paddr(T, L, phase, c)];
+    // end formula on (h1, h2, m1, m2) measured from the end node inwards; orientation-independent
+    const double h1 = fabs(xb - xa), h2 = fabs(xc - xb);
+    const double sg = (xb > xa) ? 1.0 : -1.0;
+    const double m1 = sg * (yb - ya) * (1.0 / h1), m2 = sg * (yc - yb) * (1.0 / h2);
+    double d = fma(fma(2.0, h1, h2), m1, -(h1 * m2)) * (1.0 / (h1 + h2));
+    if (m1 * m2 < 0.0 || m1 == 0.0 || m2 == 0.0) d = 0.0;
+    return d;
+  }
+  const double xm = X[paddr(T, L, phase, i - 1)], x0 = X[paddr(T, L, phase, i)], xp = X[paddr(T, L, phase, i + 1)];
+  const double ym = C[paddr(T, L, phase, i - 1)], y0 = C[paddr(T, L, phase, i)], yp = C[paddr(T, L, phase, i + 1)];
+  const double ihm = frcp_(x0 - xm), ihp = frcp_(xp - x0);           // both negative for the reversed phase: cancels
+  return slope_interior(fabs(ihm), fabs(ihp), (y0 - ym) * ihm, (yp - y0) * ihp);
+}
+
+template <int T, int NDIM>
+__global__ void __launch_bounds__(T, 2) mbm_stream_kernel(const KArgs A, const int member0) {
+  __shared__ Scal S;
+  __shared__ double redS[T], redD[T], redU[T], red0[T], red1[T];
+  __shared__ double exA[T], exG[T], exR[T];
+  __shared__ StreamLayout Lcur, Lnew;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int mem = member0 + blockIdx.x;
+  if (mem >= A.M) return;
+  const int MC = A.kcapL;                     // rows per column capacity of the workspace
+  const size_t ASZ = (size_t)MC * T;
+  double *base = A.workspace + (size_t)blockIdx.x * 6 * ASZ;
+  double *X = base, *C = base + ASZ, *FA = base + 2 * ASZ, *FG = base + 3 * ASZ, *Xn = base + 4 * ASZ, *Cn = base + 5 * ASZ;
+  const int bc = A.inner_bc;
+  const bool mb = (bc == BC_MB);
+  MemberPtrs P;
+  P.t_ar = A.t_ar + (size_t)mem * A.t_stride;
+  P.T_ar = A.T_ar + (size_t)mem * A.T_stride;
+  P.KD_ar = A.KD_ar + (size_t)mem * A.KD_stride;
+
+  // ---------------- load member ----------------
+  if (tid == 0) {
+    S.status = A.status[mem];
+    S.warn = 0;
+    S.t = A.t[mem]; S.dt = A.dt[mem]; S.it = A.it[mem]; S.steps = 0;
+    S.t_tot = A.t_tot[mem]; S.CFL = A.CFL[mem];
+    S.Di0 = A.Di[2 * (size_t)mem]; S.Di1 = A.Di[2 * (size_t)mem + 1];
+    S.D00 = A.D0 ? A.D0[2 * (size_t)mem] : 0.0; S.D01 = A.D0 ? A.D0[2 * (size_t)mem + 1] : 0.0;
+    S.Ea0 = A.Ea ? A.Ea[2 * (size_t)mem] : 0.0; S.Ea1 = A.Ea ? A.Ea[2 * (size_t)mem + 1] : 0.0;
+    S.R = A.R;
+    S.arrhenius = (S.Di0 == -1.0 && S.Di1 == -1.0);
+    S.bc0 = A.BCout[2 * (size_t)mem]; S.bc1 = A.BCout[2 * (size_t)mem + 1];
+    S.hash = A.idx_hash ? A.idx_hash[mem] : 0ull;
+    S.node_steps = A.node_steps ? A.node_steps[mem] : 0;
+    S.hidx = 0; S.Fl = 0; S.KD = 0.0; S.T = 0.0; S.D_l = 0.0; S.D_r = 0.0;
+    S.n1 = (int)A.res[2 * (size_t)mem]; S.n2 = (int)A.res[2 * (size_t)mem + 1];
+    S.rho1 = A.rho[2 * (size_t)mem]; S.rho2 = A.rho[2 * (size_t)mem + 1];
+    S.V = A.V_ip ? A.V_ip[mem] : 0.0;
+    S.MRefin = A.MRefin[mem];
+    S.resmin1 = A.resmin[2 * (size_t)mem]; S.resmin2 = A.resmin[2 * (size_t)mem + 1];
+    S.Ri1 = A.Ri[2 * (size_t)mem]; S.Ri2 = A.Ri[2 * (size_t)mem + 1];
+    S.Mass0 = A.Mass0 ? A.Mass0[mem] : 0.0;
+    S.newton_R = A.newton_R ? A.newton_R[mem] : 0.0;
+    bool mine = A.only_deferred ? (S.status == -1) : (S.status == 0);
+    // columns: m nodes each; both phases plus one appended node must fit T columns of MC rows
+    const int mneed = (S.n1 + S.n2 + 2 + (T - 3)) / (T - 2);
+    const bool ok = (S.V != 0.0) && (S.MRefin == 1.0) && S.n1 >= 3 && S.n2 >= 3 && mneed <= MC;
+    if (mine && !ok) { if (!A.only_deferred) A.status[mem] = -1; mine = false; }
+    if (mine) S.status = 0;
+    S.use_chain = mine ? 1 : 0;
+    if (mine && A.only_deferred && A.steps_done) S.steps = A.steps_done[mem];
+    if (mine) { Lcur.m = mneed; Lcur.colR0 = (S.n1 + 1 + mneed - 1) / mneed; }
+  }
+  __syncthreads();
+  if (!S.use_chain) return;
+  {
+    const int n1 = S.n1, n2 = S.n2;
+    const StreamLayout L = Lcur;
+    const double *gxl = A.x_left + (size_t)mem * A.capL, *gcl = A.C_left + (size_t)mem * A.capL;
+    const double *gxr = A.x_right + (size_t)mem * A.capR, *gcr = A.C_right + (size_t)mem * A.capR;
+    for (int i = tid; i < n1; i += T) { const size_t a = paddr(T, L, 0, i); X[a] = gxl[i]; C[a] = gcl[i]; }
+    for (int i = tid; i < n2; i += T) { const size_t a = paddr(T, L, 1, n2 - 1 - i); X[a] = gxr[i]; C[a] = gcr[i]; }
+    double v[4] = {1e300, -1e300, 1e300, -1e300}, tm[2] = {1e300, -1e300};
+    for (int i = tid; i < A.hist_len; i += T) {
+      const double tt = P.t_ar[i], TT = P.T_ar[i], kd = P.KD_ar[i];
+      tm[0] = fmin(tm[0], tt); tm[1] = fmax(tm[1], tt);
+      v[2] = fmin(v[2], TT); v[3] = fmax(v[3], TT);
+      v[0] = fmin(v[0], kd); v[1] = fmax(v[1], kd);
+    }
+    v[0] = warp_min(v[0]); v[1] = warp_max(v[1]); v[2] = warp_min(v[2]); v[3] = warp_max(v[3]);
+    tm[0] = warp_min(tm[0]); tm[1] = warp_max(tm[1]);
+    if (lane == 0) { redS[wid] = v[0]; redD[wid] = v[1]; redU[wid] = v[2]; red0[wid] = v[3]; red1[wid] = tm[0]; exA[wid] = tm[1]; }
+    __syncthreads();
+    if (tid == 0) {
+      double a0 = 1e300, a1 = -1e300, a2 = 1e300, a3 = -1e300, a4 = 1e300, a5 = -1e300;
+#pragma unroll 1
+      for (int k = 0; k < T / 32; ++k) {
+        a0 = fmin(a0, redS[k]); a1 = fmax(a1, redD[k]); a2 = fmin(a2, redU[k]); a3 = fmax(a3, red0[k]);
+        a4 = fmin(a4, red1[k]); a5 = fmax(a5, exA[k]);
+      }
+      S.KDmin = a0; S.KDmax = a1; S.Tmin = a2; S.Tmax = a3; S.tmin = a4; S.tmax = a5;
+      S.dx1 = xsub(gxl[n1 - 1], gxl[n1 - 2]);                                // create_grid!, functions.jl:366-367
+      S.dx2 = xsub(gxr[1], gxr[0]);
+      const int rc = update_t_dependent(S, A, P, false);
+      if (rc) S.status = rc;
+    }
+  }
+  __syncthreads();
+
+  unsigned long long hash_local = 0ull;
+  const bool do_hash = (A.idx_hash != nullptr);
+  HistCache hc;
+  if (tid == 0) hist_load(hc, P, S.hidx);
+
+  while (true) {
+    if (S.status != 0 || !(S.t < S.t_tot) || (A.max_steps > 0 && S.steps >= A.max_steps)) break;
+    __syncthreads();
+    // ---------------- scalar phase (thread 0): dt, time, parameters, interface advection, new node counts ---------------
+    if (tid == 0) {
+      const StreamLayout L = Lcur;
+      double dt;
+      if (A.dt_mode == DT_ADV) dt = xmul(xdiv(fmin(S.dx1, S.dx2), S.V), S.CFL);                 // C1.jl:93
+      else {                                                                                      // find_dt :465-490
+        const double mn = fmin(S.dx1, S.dx2), mxD = fmax(S.D_l, S.D_r);
+        double dtV = xmul(mn, xinv(fabs(S.V)));
+        const double dtD = xmul(xmul(xmul(mn, mn), xinv(mxD)), 50.0);
+        dtV = xmul(dtV, 0.99);
+        dt = (dtV < dtD) ? xmul(dtV, S.CFL) : xmul(dtD, S.CFL);
+      }
+      S.dt = dt;
+      S.t = xadd(S.t, S.dt);
+      S.it += 1;
+      if (S.t > S.t_tot) { S.dt = xsub(S.dt, xsub(S.t, S.t_tot)); S.t = S.t_tot; }
+      double KD, Tt, Dl, Dr;
+      int rc = chain_update_params(S, A, P, S.t, hc, &KD, &Tt, &Dl, &Dr);
+      if (!rc) {
+        S.KD = KD; S.T = Tt; S.D_l = Dl; S.D_r = Dr;
+        const int n1 = S.n1, n2 = S.n2;
+        const double Rnew = xadd(S.Ri1, xmul(S.V, S.dt));                                        // functions.jl:31
+        if (S.V > 0.0) {
+          if (n1 + 1 > A.capL) rc = 10;
+          else {
+            S.Ri1 = Rnew;
+            if (Rnew > X[paddr(T, L, 1, n2 - 2)]) rc = 1;                                         // x_right[2], :37-40
+            else {
+              X[paddr(T, L, 0, n1)] = Rnew; C[paddr(T, L, 0, n1)] = C[paddr(T, L, 0, n1 - 1)];    // :33-35
+              X[paddr(T, L, 1, n2 - 1)] = Rnew;                                                   // :41
+              S.n1 = n1 + 1;
+            }
+          }
+        } else {
+          if (n2 + 1 > A.capR) rc = 10;
+          else {
+            S.Ri1 = Rnew;
+            if (Rnew < X[paddr(T, L, 0, n1 - 2)]) rc = 2;                                         // x_left[end-1], :50-53
+            else {
+              X[paddr(T, L, 1, n2)] = Rnew; C[paddr(T, L, 1, n2)] = C[paddr(T, L, 1, n2 - 1)];    // :46-48 (append in reversed order)
+              X[paddr(T, L, 0, n1 - 1)] = Rnew;                                                   // :54
+              S.n2 = n2 + 1;
+            }
+          }
+        }
+      }
+      if (!rc) {                                                                                  // regrid! :873-889
+        long long nr1 = S.n1, nr2 = S.n2;
+        if (S.V > 0.0) nr1 = (long long)rint(xmul(xmul(S.Ri1, xinv(xsub(S.Ri2, S.Ri1))), (double)nr2));
+        else nr2 = (long long)rint(xmul(xmul(S.Ri2, xinv(xsub(S.Ri2, S.Ri1))), (double)nr1));
+        if (nr1 < S.resmin1) nr1 = S.resmin1;
+        if (nr2 < S.resmin2) nr2 = S.resmin2;
+        if (nr1 > A.capL || nr2 > A.capR || nr1 < 3 || nr2 < 3) rc = 10;
+        else {
+          const int mneed = (int)((nr1 + nr2 + 2 + (T - 3)) / (T - 2));
+          if (mneed > MC) rc = 10;
+          else { Lnew.m = mneed; Lnew.colR0 = (int)((nr1 + 1 + mneed - 1) / mneed); S.nr1 = (int)nr1; S.nr2 = (int)nr2; }
+        }
+      }
+      if (rc) S.status = rc; else S.node_steps += S.n1 + S.n2;
+    }
+    __syncthreads();
+    if (S.status != 0) break;
+
+    // ---------------- solve ------------------------------------------------------------------------------------------------
+    const StreamLayout L = Lcur;
+    const int n1 = S.n1, n2 = S.n2, m = L.m;
+    const double idt = frcp_(S.dt);
+    // thread t owns column t; its sweep rows are its nodes except the phase's last node (the interface node)
+    const int KL = (n1 - 1 + m - 1) / m, KR = (n2 - 1 + m - 1) / m;       // columns with sweep rows
+    const int blk = (tid >= L.colR0) ? 1 : 0;
+    const int jc = blk ? (tid - L.colR0) : tid;
+    const int nph = blk ? n2 : n1;
+    const bool active = blk ? (jc < KR) : (jc < KL);
+    const int f = jc * m;                                                   // first phase-ordered index of the column
+    const int len = active ? (min(f + m, nph - 1) - f) : 0;
+    const bool lastChunk = active && (jc == (blk ? KR : KL) - 1);
+    const double Dph = blk ? S.D_r : S.D_l;
+    const bool dir0 = (blk ? (S.bc1 == 1) : (S.bc0 == 1)) && f == 0;
+    const double Co_out = X == nullptr ? 0.0 : C[paddr(T, L, blk, 0)];      // old value at the outer boundary of this phase
+    const double a_old = C[paddr(T, L, 0, n1 - 1)], b_old = C[paddr(T, L, 1, n2 - 1)];
+    (void)a_old; (void)b_old;
+    double Ap = 0.0, Gp = 0.0, Rp = 0.0, P0 = 0.0, Qa = 0.0, Qc = 0.0;
+    double bA = 0.0, bG = -1.0, bR = 0.0;
+    // halo values must be read before any thread overwrites C in place
+    double c_halo_prev = 0.0, c_halo_next = 0.0, x_halo_prev = 0.0, x_halo_next = 0.0;
+    if (active) {
+      if (f > 0) { x_halo_prev = X[paddr(T, L, blk, f - 1)]; c_halo_prev = C[paddr(T, L, blk, f - 1)]; }
+      x_halo_next = X[paddr(T, L, blk, f + len)]; c_halo_next = C[paddr(T, L, blk, f + len)];
+    }
+    __syncthreads();
+    if (active) {
+      // forward sweep over the column (coalesced: element k of column t at k*T + t)
+      const int SDp = blk ? -1 : 1;        // orientation of x along the sweep: left increasing, right (reversed) decreasing
+      double x_self = X[saddr(T, tid, 0)], c_self = C[saddr(T, tid, 0)];
+      double x_prev = x_halo_prev, c_prev = c_halo_prev;
+      double pAc = 0.0, pAnext = 0.0, pkk = 0.0;
+      const bool haveP0 = f > 0;
+      if (haveP0) {
+        double A11, A12, A22, kk;
+        if (SDp > 0) elem_mats_fast<NDIM>(x_prev, x_self, Dph, idt, A11, A12, A22, kk);
+        else elem_mats_fast<NDIM>(x_self, x_prev, Dph, idt, A11, A12, A22, kk);
+        pAnext = (SDp > 0) ? A22 : A11; pAc = A12; pkk = kk;
+      }
+      double Qb = 0.0, Vs = 0.0, Vm = 0.0;
+      if (mb) { Vs = powd<NDIM>(x_self); Vm = haveP0 ? powd<NDIM>(x_prev) : Vs; }
+      double xn_pf = (len > 1) ? X[saddr(T, tid, 1)] : x_halo_next, cn_pf = (len > 1) ? C[saddr(T, tid, 1)] : c_halo_next;
+#pragma unroll 1
+      for (int k = 0; k < len; ++k) {
+        const double x_next = xn_pf, c_next = cn_pf;
+        if (k + 2 < len) { xn_pf = X[saddr(T, tid, k + 2)]; cn_pf = C[saddr(T, tid, k + 2)]; }   // prefetch one row ahead
+        else { xn_pf = x_halo_next; cn_pf = c_halo_next; }
+        double A11, A12, A22, kk;
+        if (SDp > 0) elem_mats_fast<NDIM>(x_self, x_next, Dph, idt, A11, A12, A22, kk);
+        else elem_mats_fast<NDIM>(x_next, x_self, Dph, idt, A11, A12, A22, kk);
+        const double nAself = (SDp > 0) ? A11 : A22, nAnext = (SDp > 0) ? A22 : A11;
+        double diag = (nAself - kk) + (pAnext - pkk);
+        double rhs = (nAself * c_self + A12 * c_next) + (pAc * c_prev + pAnext * c_self);
+        double sup = A12 + kk, sub = pAc + pkk;
+        if (dir0 && k == 0) { diag = 1.0; rhs = Co_out; sup = 0.0; sub = 0.0; }
+        const double inv = frcp_(diag - sub * Gp);
+        const double An = (k == 0) ? (sub * inv) : (-sub * Ap * inv);
+        const double Gn = sup * inv;
+        const double Rn = (rhs - sub * Rp) * inv;
+        const size_t a = saddr(T, tid, k);
+        FA[a] = An; FG[a] = Gn; C[a] = Rn;
+        if (mb) {
+          const double Vn = powd<NDIM>(x_next);
+          const double wgt = 0.5 * fabs(Vn - Vs) + 0.5 * fabs(Vs - Vm);
+          if (k < len - 1) { const double tq = Qb + wgt; P0 = fma(tq, Rn, P0); Qa = fma(-tq, An, Qa); Qb = -tq * Gn; }
+          else Qc = Qb + wgt;
+          Vm = Vs; Vs = Vn;
+        }
+        Ap = An; Gp = Gn; Rp = Rn;
+        x_prev = x_self; c_prev = c_self; x_self = x_next; c_self = c_next;
+        pAc = A12; pAnext = nAnext; pkk = kk;
+      }
+      // backward accumulation (division-free): first row of the column in terms of the two separators
+      if (len > 1) {
+        size_t a = saddr(T, tid, len - 2);
+        bA = FA[a]; bG = FG[a]; bR = C[a];
+#pragma unroll 1
+        for (int k = len - 3; k >= 0; --k) {
+          a -= T;
+          const double Gk = FG[a];
+          bR = C[a] - Gk * bR; bA = FA[a] - Gk * bA; bG = -Gk * bG;
+        }
+      }
+    }
+    exA[tid] = bA; exG[tid] = bG; exR[tid] = bR;
+    __syncthreads();
+    if (active) {
+      if (!lastChunk) {
+        const double nA = exA[tid + 1], nG = exG[tid + 1], nR = exR[tid + 1];
+        redS[tid] = Ap; redD[tid] = 1.0 - Gp * nA; redU[tid] = -Gp * nG; red0[tid] = Rp - Gp * nR; red1[tid] = 0.0;
+      } else { redS[tid] = Ap; redD[tid] = 1.0; redU[tid] = 0.0; red0[tid] = Rp; red1[tid] = -Gp; }
+    } else { redS[tid] = 0.0; redD[tid] = 1.0; redU[tid] = 0.0; red0[tid] = 0.0; red1[tid] = 0.0; }
+    __syncthreads();
+    if (tid < 32) reduced_solve<T>(redS, redD, redU, red0, red1);
+    __syncthreads();
+    // interface condition (nodes next to the interface: phase-ordered n-2 and n-3)
+    double aif, bif;
+    {
+      const double xp_ = X[paddr(T, L, 0, n1 - 1)], xq_ = X[paddr(T, L, 1, n2 - 1)];
+      const double xpm = X[paddr(T, L, 0, n1 - 2)], xqp = X[paddr(T, L, 1, n2 - 2)];
+      const int rL = KL - 1, rR = L.colR0 + KR - 1;                         // reduced rows of the last chunks
+      if (bc == BC_FLUX) {
+        const double idxl = frcp_(xp_ - xpm), idxr = frcp_(xqp - xq_);
+        const double al = -S.rho1 * S.D_l * idxl, be = S.V * S.rho1 + S.rho1 * S.D_l * idxl;
+        const double ga = -S.V * S.rho2 + S.rho2 * S.D_r * idxr, de = -S.rho2 * S.D_r * idxr;
+        const double ca = be + al * red1[rL], cb = ga + de * red1[rR];
+        bif = -(al * red0[rL] + de * red0[rR]) / (ca * S.KD + cb);
+        aif = S.KD * bif;
+      } else {
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        if (active) {
+          const double s0v = red0[tid], s1v = red1[tid];
+          const double q0 = (jc > 0) ? red0[tid - 1] : 0.0, q1 = (jc > 0) ? red1[tid - 1] : 0.0;
+          const double c0 = P0 + Qa * q0 + Qc * s0v, c1 = Qa * q1 + Qc * s1v;
+          if (blk == 0) { v[0] = c0; v[1] = c1; } else { v[2] = c0; v[3] = c1; }
+        }
+        block_sum4<T>(v, S.red);
+        const double Vp_ = powd<NDIM>(xp_), Vq_ = powd<NDIM>(xq_);
+        const double wp = 0.5 * (Vq_ - Vp_) + 0.5 * (Vp_ - powd<NDIM>(xpm));
+        const double wq = 0.5 * (powd<NDIM>(xqp) - Vq_) + 0.5 * (Vq_ - Vp_);
+        bif = (S.Mass0 - (v[0] + v[2])) / ((v[1] + wp) * S.KD + (v[3] + wq));
+        aif = S.KD * bif;
+      }
+    }
+    if (active) {
+      const double beta = blk ? bif : aif;
+      const double sj = red0[tid] + red1[tid] * beta;
+      const double sp = (jc > 0) ? (red0[tid - 1] + red1[tid - 1] * beta) : 0.0;
+      double cn = sj;
+      size_t a = saddr(T, tid, len - 1);
+      C[a] = cn;
+#pragma unroll 2
+      for (int k = len - 2; k >= 0; --k) { a -= T; cn = C[a] - FA[a] * sp - FG[a] * cn; C[a] = cn; }
+    }
+    if (tid == 0) { C[paddr(T, L, 0, n1 - 1)] = aif; C[paddr(T, L, 1, n2 - 1)] = bif; }
+    __threadfence_block();
+    __syncthreads();
+
+    // ---------------- regrid (MRefin == 1: two LinRanges, functions.jl:396-400) + pchip ------------------------------------
+    {
+      const StreamLayout LN = Lnew;
+      const int nr1 = S.nr1, nr2 = S.nr2;
+      const double Ri1 = S.Ri1, Ri2 = S.Ri2;
+      // thread t fills column t of the NEW layout: nodes idx0..idx0+cnt-1 of one phase in phase order
+      const int nblk = (tid >= LN.colR0) ? 1 : 0;
+      const int ncol = nblk ? (tid - LN.colR0) : tid;
+      const int nn = nblk ? nr2 : nr1;          // new node count of the phase
+      const int no = nblk ? n2 : n1;            // old node count of the phase
+      const int idx0 = ncol * LN.m;
+      const int cnt = max(0, min(idx0 + LN.m, nn) - idx0);
+      int c = -1;                               // phase-ordered count of old nodes "before" the new node
+      double xa = 0.0, xb = 0.0;                // old nodes c-1 and c (phase order)
+      for (int k = 0; k < cnt; ++k) {
+        const int pi = idx0 + k;                                  // phase-ordered index of the new node
+        const int j = nblk ? (nn - 1 - pi) : pi;                  // node index in the reference's order
+        const double Xj = nblk ? linrange_at(Ri1, Ri2, nn, j) : linrange_at(0.0, Ri1, nn, j);
+        // walk in phase order.  Left: c = #old nodes with x < Xj.  Right (reversed order, x decreasing with index):
+        // c = #old nodes with x > Xj, i.e. the first old index whose x is <= Xj.
+        if (c < 0) {
+          c = min(max((int)(((long long)pi * no) / nn), 1), no - 1);
+          xa = X[paddr(T, L, nblk, c - 1)]; xb = X[paddr(T, L, nblk, c)];
+        }
+        int steps = 0;
+        if (!nblk) {
+          while (c < no && xb < Xj) { ++c; xa = xb; xb = (c < no) ? X[paddr(T, L, 0, c)] : xb; if (++steps > 64) break; }
+          while (c > 0 && !(xa < Xj) && steps <= 64) { --c; xb = xa; xa = (c > 0) ? X[paddr(T, L, 0, c - 1)] : xa; ++steps; }
+          if (steps > 64) {
+            int lo = 0, hi = no;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (X[paddr(T, L, 0, mid)] < Xj) lo = mid + 1; else hi = mid; }
+            c = lo; xa = (c > 0) ? X[paddr(T, L, 0, c - 1)] : 0.0; xb = (c < no) ? X[paddr(T, L, 0, c)] : 0.0;
+          }
+        } else {
+          while (c < no && xb > Xj) { ++c; xa = xb; xb = (c < no) ? X[paddr(T, L, 1, c)] : xb; if (++steps > 64) break; }
+          while (c > 0 && !(xa > Xj) && steps <= 64) { --c; xb = xa; xa = (c > 0) ? X[paddr(T, L, 1, c - 1)] : xa; ++steps; }
+          if (steps > 64) {
+            int lo = 0, hi = no;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (X[paddr(T, L, 1, mid)] > Xj) lo = mid + 1; else hi = mid; }
+            c = lo; xa = (c > 0) ? X[paddr(T, L, 1, c - 1)] : 0.0; xb = (c < no) ? X[paddr(T, L, 1, c)] : 0.0;
+          }
+        }
+        // reference semantics (functions.jl:809-837) in the reference's node order (fwd index = no-1-idx for the right phase)
+        double Pj; int kk, br;
+        if (!nblk) {
+          if (c < no && xb == Xj) { kk = c; br = 0; Pj = C[paddr(T, L, 0, c)]; }
+          else if (c == no) { kk = no - 1; br = 1; Pj = C[paddr(T, L, 0, no - 1)]; }
+          else if (c == 0) { kk = 0; br = 2; Pj = C[paddr(T, L, 0, 0)]; }
+          else {
+            kk = c - 1; br = 3;
+            const double y1 = C[paddr(T, L, 0, c - 1)], y2 = C[paddr(T, L, 0, c)];
+            const double d1 = stream_slope<T>(X, C, L, 0, no, c - 1), d2 = stream_slope<T>(X, C, L, 0, no, c);
+            const double h = xb - xa, ih = frcp_(h), s = Xj - xa, u = s * ih, smh = s - h, u2 = u * u, w2 = u2 * (3.0 - 2.0 * u);
+            Pj = w2 * y2 + (1.0 - w2) * y1 + (u2 * smh) * d2 + (u * smh) * (smh * ih) * d1;
+          }
+        } else {
+          // reversed phase: old idx c-1 has x = xa > Xj >= xb = x of idx c (or c == no: Xj below all; c == 0: above all)
+          if (c < no && xb == Xj) { kk = no - 1 - c; br = 0; Pj = C[paddr(T, L, 1, c)]; }
+          else if (c > 0 && xa == Xj) { kk = no - c; br = 0; Pj = C[paddr(T, L, 1, c - 1)]; }
+          else if (c == 0) { kk = no - 1; br = 1; Pj = C[paddr(T, L, 1, 0)]; }                   // X > max(x): value at the max
+          else if (c == no) { kk = 0; br = 2; Pj = C[paddr(T, L, 1, no - 1)]; }                   // X < min(x)
+          else {
+            kk = no - 1 - c; br = 3;                                                              // fwd interval [x_fwd[kk], x_fwd[kk+1]] = [xb, xa]
+            const double y1 = C[paddr(T, L, 1, c)], y2 = C[paddr(T, L, 1, c - 1)];
+            const double d1 = stream_slope<T>(X, C, L, 1, no, c), d2 = stream_slope<T>(X, C, L, 1, no, c - 1);
+            const double h = xa - xb, ih = frcp_(h), s = Xj - xb, u = s * ih, smh = s - h, u2 = u * u, w2 = u2 * (3.0 - 2.0 * u);
+            Pj = w2 * y2 + (1.0 - w2) * y1 + (u2 * smh) * d2 + (u * smh) * (smh * ih) * d1;
+          }
+        }
+        const size_t an = saddr(T, tid, k);
+        Xn[an] = Xj; Cn[an] = Pj;
+        if (do_hash) hash_local += idx_term(S.it, nblk, j, kk, br);
+      }
+    }
+    __threadfence_block();
+    __syncthreads();
+    { double *tp = X; X = Xn; Xn = tp; tp = C; C = Cn; Cn = tp; }
+    if (tid == 0) {
+      S.n1 = S.nr1; S.n2 = S.nr2;
+      Lcur = Lnew;
+      S.dx1 = xsub(linrange_at(0.0, S.Ri1, S.n1, S.n1 - 1), linrange_at(0.0, S.Ri1, S.n1, S.n1 - 2));   // regrid! :893-894
+      S.dx2 = xsub(linrange_at(S.Ri1, S.Ri2, S.n2, 1), linrange_at(S.Ri1, S.Ri2, S.n2, 0));
+      S.steps += 1;
+      const double cf = C[paddr(T, Lnew, 0, 0)], cl = C[paddr(T, Lnew, 1, 0)], ci = C[paddr(T, Lnew, 0, S.n1 - 1)];
+      if (!isfinite(cf) || !isfinite(cl) || !isfinite(ci) || !isfinite(S.Ri1)) S.status = 11;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  // ---------------- store member ----------------
+  {
+    const StreamLayout L = Lcur;
+    const int n1 = S.n1, n2 = S.n2;
+    double *gxl = A.x_left + (size_t)mem * A.capL, *gcl = A.C_left + (size_t)mem * A.capL;
+    double *gxr = A.x_right + (size_t)mem * A.capR, *gcr = A.C_right + (size_t)mem * A.capR;
+    for (int i = tid; i < n1 && i < A.capL; i += T) { const size_t a = paddr(T, L, 0, i); gxl[i] = X[a]; gcl[i] = C[a]; }
+    for (int i = tid; i < n2 && i < A.capR; i += T) { const size_t a = paddr(T, L, 1, n2 - 1 - i); gxr[i] = X[a]; gcr[i] = C[a]; }
+    if ((A.flags & F_MASS_FINAL) && A.Mass) {
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int i = tid; i < n1 - 1; i += T) {
+        const size_t a = paddr(T, L, 0, i), b = paddr(T, L, 0, i + 1);
+        v[0] += 0.5 * (S.rho1 * powd<NDIM>(X[b]) - S.rho1 * powd<NDIM>(X[a])) * (C[a] + C[b]);
+      }
+      for (int i = tid; i < n2 - 1; i += T) {
+        const size_t a = paddr(T, L, 1, n2 - 1 - i), b = paddr(T, L, 1, n2 - 2 - i);
+        v[1] += 0.5 * (S.rho2 * powd<NDIM>(X[b]) - S.rho2 * powd<NDIM>(X[a])) * (C[a] + C[b]);
+      }
+      block_sum4<T>(v, S.red);
+      if (tid == 0) A.Mass[mem] = v[0] + v[1];
+    }
+    if (A.idx_hash) {
+      unsigned long long h = hash_local;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+      if (lane == 0) atomicAdd(&S.hash, h);
+      __syncthreads();
+    }
+    if (tid == 0) {
+      A.status[mem] = S.status;
+      if (A.steps_done) A.steps_done[mem] = S.steps;
+      if (A.warn) A.warn[mem] = S.warn;
+      A.t[mem] = S.t; A.dt[mem] = S.dt; A.it[mem] = S.it;
+      A.res[2 * (size_t)mem] = n1; A.res[2 * (size_t)mem + 1] = n2;
+      A.Ri[2 * (size_t)mem] = S.Ri1; A.Ri[2 * (size_t)mem + 1] = S.Ri2;
+      if (A.dx1) A.dx1[mem] = S.dx1;
+      if (A.dx2) A.dx2[mem] = S.dx2;
+      if (A.newton_R) A.newton_R[mem] = S.newton_R;
+      if (A.last) {
+        double *Lq = A.last + 8 * (size_t)mem;
+        Lq[0] = S.D_l; Lq[1] = S.D_r; Lq[2] = S.KD; Lq[3] = S.T; Lq[4] = S.V; Lq[5] = S.rho1; Lq[6] = S.rho2; Lq[7] = 1.0;
+      }
+      if (A.idx_hash) A.idx_hash[mem] = S.hash;
+      if (A.node_steps) A.node_steps[mem] = S.node_steps;
+    }
+  }
+}
+
+}  // namespace mbm

@@ -278,3 +278,22 @@ def test_whole_run_MB_growth(oracle, cuda_lib):
     compare(eo, eg, tol=5e-10)
     assert int(eg.it[0]) == 9352 and list(eg.res[0]) == [200, 398]
     assert abs((eg.Mass[0] - eg.Mass0[0]) / eg.Mass0[0]) < 1e-10
+
+
+@pytest.mark.parametrize("kind", ["mb", "flux"])
+def test_streaming_interleaved_kernel(oracle, cuda_lib, kind):
+    """the chunk-interleaved global-memory kernel (long profiles, MRefin = 1: config 5's shape) against the oracle:
+    growth and resorption members, node counts that change during the run"""
+    pars = []
+    for V, res in ((1e-7, [300, 500]), (-1e-7, [300, 500]), (2e-7, [257, 258]), (-3e-7, [400, 401])):
+        p = d.pars_MB_growth() if kind == "mb" else d.pars_DCGF()
+        p.update(V_ip=V, res=res, MRefin=1.0, Ri=[0.45, 1.0], t_tot=2e4, KD_ar=(0.1, 0.1), Cl_i=0.5, Cr_i=5.0)
+        if kind == "flux":
+            p.update(n=2, Di=[4e-7, 5e-8], T_ar=(1273.15, 923.15))
+        pars.append(p)
+    eo, _ = d.build_couple_ensemble(pars, oracle, cap_left=1200, cap_right=1600)
+    eg, _ = d.build_couple_ensemble(pars, cuda_lib, cap_left=1200, cap_right=1600)
+    assert np.array_equal(eo.x_left, eg.x_left) and np.array_equal(eo.x_right, eg.x_right)
+    assert eo.run(oracle, max_steps=120) == 0
+    assert eg.run(cuda_lib, max_steps=120, flags=abi.FLAG_FORCE_STREAMING) == 0
+    compare(eo, eg)
