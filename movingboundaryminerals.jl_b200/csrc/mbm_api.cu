@@ -30,6 +30,13 @@ long long g_last_kernel_launches_any = 0;
     }                                                                                              \
   } while (0)
 
+// launch-site check that says what failed (no silent MBM_RC_CUDA)
+int launch_rc(const char *what, cudaError_t e) {
+  if (e == cudaSuccess) return 0;
+  fprintf(stderr, "[mbm_b200] %s failed: %s (%s)\n", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return MBM_RC_CUDA;
+}
+
 // staging of one shard: device copies of host arrays, copied back on request
 struct Stage {
   struct Item { void *h; void *d; size_t bytes; bool out; };
@@ -48,7 +55,7 @@ struct Stage {
     if (e != cudaSuccess) { rc = (e == cudaErrorMemoryAllocation) ? MBM_RC_OOM : MBM_RC_CUDA; return nullptr; }
     owned.push_back(d);
     e = cudaMemcpyAsync(d, h, count * sizeof(Tp), cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess) { rc = MBM_RC_CUDA; return nullptr; }
+    if (e != cudaSuccess) { rc = MBM_RC_CUDA; fprintf(stderr, "[mbm_b200] host-to-device copy failed: %s\n", cudaGetErrorString(e)); return nullptr; }
     items.push_back({(void *)h, d, count * sizeof(Tp), out});
     return (Tp *)d;
   }
@@ -77,7 +84,7 @@ struct Stage {
     for (auto &it : items)
       if (it.out) {
         cudaError_t e = cudaMemcpyAsync(it.h, it.d, it.bytes, cudaMemcpyDeviceToHost, stream);
-        if (e != cudaSuccess) return MBM_RC_CUDA;
+        if (e != cudaSuccess) return launch_rc("device-to-host copy", e);
       }
     return 0;
   }
@@ -103,20 +110,18 @@ template <int T>
 int launch_T(const mbm::KArgs &A, int member0, int count, bool use_global, size_t smem_bytes, cudaStream_t s) {
   auto kern = mbm::mbm_step_kernel<T>;
   if (!use_global) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return MBM_RC_CUDA;
+    if (int rc = launch_rc("general kernel: shared-memory opt-in", cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes))) return rc;
   }
   kern<<<count, T, use_global ? 0 : smem_bytes, s>>>(A, member0);
-  return (cudaGetLastError() == cudaSuccess) ? 0 : MBM_RC_CUDA;
+  return launch_rc("general kernel launch", cudaGetLastError());
 }
 
 template <int T, int NDIM>
 int launch_v2_TN(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
   auto kern = mbm::mbm_step_kernel_v2<T, NDIM>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-  if (e != cudaSuccess) return MBM_RC_CUDA;
+  if (int rc = launch_rc("tuned kernel: shared-memory opt-in", cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes))) return rc;
   kern<<<count, T, smem_bytes, s>>>(A, member0);
-  return (cudaGetLastError() == cudaSuccess) ? 0 : MBM_RC_CUDA;
+  return launch_rc("tuned kernel launch", cudaGetLastError());
 }
 template <int T>
 int launch_v2_T(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
@@ -130,10 +135,9 @@ int launch_v2_T(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, 
 template <int T, int NDIM>
 int launch_fixed_TN(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
   auto kern = mbm::mbm_fixed_kernel<T, NDIM>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-  if (e != cudaSuccess) return MBM_RC_CUDA;
+  if (int rc = launch_rc("fixed-interface kernel: shared-memory opt-in", cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes))) return rc;
   kern<<<count, T, smem_bytes, s>>>(A, member0);
-  return (cudaGetLastError() == cudaSuccess) ? 0 : MBM_RC_CUDA;
+  return launch_rc("fixed-interface kernel launch", cudaGetLastError());
 }
 template <int T>
 int launch_fixed_T(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
@@ -146,7 +150,7 @@ int launch_fixed_T(const mbm::KArgs &A, int member0, int count, size_t smem_byte
 template <int NDIM>
 int launch_stream_N(const mbm::KArgs &A, int member0, int count, cudaStream_t s) {
   mbm::mbm_stream_kernel<256, NDIM><<<count, 256, 0, s>>>(A, member0);
-  return (cudaGetLastError() == cudaSuccess) ? 0 : MBM_RC_CUDA;
+  return launch_rc("streaming kernel launch", cudaGetLastError());
 }
 int launch_stream(const mbm::KArgs &A, int member0, int count, cudaStream_t s) {
   switch (A.ndim) {
@@ -156,16 +160,33 @@ int launch_stream(const mbm::KArgs &A, int member0, int count, cudaStream_t s) {
   }
 }
 
+// static shared memory of one instantiation, asked from the runtime (an estimate that is a few KB short makes the
+// shared-memory opt-in fail at the largest capacities)
+template <typename K>
+int static_smem_of(K kern) {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) return 24 * 1024;
+  return (int)fa.sharedSizeBytes;
+}
+template <int T>
+int fixed_static_T(int ndim) {
+  switch (ndim) {
+    case 1: return static_smem_of(mbm::mbm_fixed_kernel<T, 1>);
+    case 2: return static_smem_of(mbm::mbm_fixed_kernel<T, 2>);
+    default: return static_smem_of(mbm::mbm_fixed_kernel<T, 3>);
+  }
+}
+
 // fixed-interface kernel: nine arrays of kF doubles per member (n1 + n2 <= kF)
-void fixed_plan(int capL, int capR, int nmax_hint, int smem_optin, int *Tf, int *kF) {
+void fixed_plan(int capL, int capR, int nmax_hint, int smem_optin, int ndim, int *Tf, int *kF) {
   int kf = capL + capR;
   if (nmax_hint > 0 && nmax_hint + 8 < kf) kf = (nmax_hint + 8) - (nmax_hint % 8);   // host buffers: size by the data
   if (const char *e = getenv("MBM_KCAP_FIXED")) { const int a = atoi(e); if (a >= 8 && a < kf) kf = a; }
   int T = 256;
   if (kf <= 320) T = 64;
   else if (kf <= 1100) T = 128;
-  const int static_est = (int)sizeof(mbm::Scal) + 8 * T * 8 + 256;
-  int kmax = (smem_optin - static_est) / (9 * 8);
+  const int stat = (T == 64) ? fixed_static_T<64>(ndim) : (T == 128) ? fixed_static_T<128>(ndim) : fixed_static_T<256>(ndim);
+  int kmax = (smem_optin - stat - 64) / (9 * 8);
   kmax -= kmax % 8;
   if (kf > kmax) kf = kmax;
   *Tf = T; *kF = kf;
@@ -173,11 +194,19 @@ void fixed_plan(int capL, int capR, int nmax_hint, int smem_optin, int *Tf, int 
 
 // combined shared-memory capacity (left | free slot | right) of the tuned kernel: as large as the caps need, within
 // two CTAs per SM (four arrays of kS doubles) and one scan tile per thread and phase (9*T nodes per phase)
-void v2_plan(int capL, int capR, int smem_per_sm, int *T2, int *kS) {
+template <int T>
+int v2_static_T(int ndim) {
+  switch (ndim) {
+    case 1: return static_smem_of(mbm::mbm_step_kernel_v2<T, 1>);
+    case 2: return static_smem_of(mbm::mbm_step_kernel_v2<T, 2>);
+    default: return static_smem_of(mbm::mbm_step_kernel_v2<T, 3>);
+  }
+}
+void v2_plan(int capL, int capR, int smem_per_sm, int ndim, int *T2, int *kS) {
   int ks = capL + capR + 1;
   if (const char *e = getenv("MBM_KCAP")) { const int a = atoi(e); if (a >= 8 && a < ks) ks = a; }
-  const int static_est = (int)sizeof(mbm::Scal) + 8 * 256 * 8 + 3 * 16 * 8 + 64;
-  const int per_cta = (smem_per_sm - 2 * 1024) / 2 - static_est;
+  const int stat = v2_static_T<256>(ndim) + 64;          // the widest instantiation bounds the others
+  const int per_cta = (smem_per_sm - 2 * 1024) / 2 - stat;
   int ks_max = per_cta / (4 * 8);
   ks_max -= ks_max % 8;
   if (ks > ks_max) ks = ks_max;
@@ -235,7 +264,7 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
   if (use_v2) {
     int smem_sm = 0;
     CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
-    v2_plan(A.capL, A.capR, smem_sm, &T2, &A.kcapL);
+    v2_plan(A.capL, A.capR, smem_sm, A.ndim, &T2, &A.kcapL);
     if (A.kcapL < 8) use_v2 = false;
   }
   if (couple_pv && !getenv("MBM_NO_CHAIN")) {
@@ -246,7 +275,7 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
   const bool use_fixed = (couple_pv || A.inner_bc == MBM_BC_DIRICHLET_HOLD) && !use_global && !getenv("MBM_NO_FIXED") &&
                          A.ndim >= 1 && A.ndim <= 3;
   int Tf = 128;
-  if (use_fixed) fixed_plan(A.capL, A.capR, A.pad3_, maxOptin, &Tf, &A.kcapR);
+  if (use_fixed) fixed_plan(A.capL, A.capR, A.pad3_, maxOptin, A.ndim, &Tf, &A.kcapR);
   if ((use_fixed || use_stream) && !use_v2) {
     A.steps_done = (long long *)st->scratch((size_t)count * sizeof(long long));
     if (!A.steps_done) return st->rc ? st->rc : MBM_RC_OOM;
@@ -427,7 +456,7 @@ int couple_shard(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io 
   if (!rc) rc = launch_shard(A, 0, (int)n, device, c->flags, st.stream, &st, ksec);
   const bool async = g_have_user_stream && st.device_ptrs;
   if (!rc) rc = st.copy_back();
-  if (!async && !rc && cudaStreamSynchronize(st.stream) != cudaSuccess) rc = MBM_RC_CUDA;
+  if (!async && !rc) rc = launch_rc("stream synchronisation after the kernels", cudaStreamSynchronize(st.stream));
   st.release();
   if (!async) cudaStreamSynchronize(st.stream);
   if (own_stream) cudaStreamDestroy(st.stream);
@@ -474,7 +503,7 @@ int simple_shard(const mbm_common *c, const mbm_simple_params *p, mbm_simple_io 
   if (!rc) rc = launch_shard(A, 0, (int)n, device, c->flags, st.stream, &st, ksec);
   const bool async = g_have_user_stream && st.device_ptrs;
   if (!rc) rc = st.copy_back();
-  if (!async && !rc && cudaStreamSynchronize(st.stream) != cudaSuccess) rc = MBM_RC_CUDA;
+  if (!async && !rc) rc = launch_rc("stream synchronisation after the kernels", cudaStreamSynchronize(st.stream));
   st.release();
   if (!async) cudaStreamSynchronize(st.stream);
   if (own_stream) cudaStreamDestroy(st.stream);

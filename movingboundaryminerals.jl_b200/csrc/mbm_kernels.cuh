@@ -73,6 +73,7 @@ struct Scal {
   unsigned long long hash;
   int n1, n2, gap, nr1, nr2, Fl, status, warn, bc0, bc1, hidx, arrhenius;
   int m, KL, KR, nbL, nbR;
+  int mq, KLq, KRq, nqL, nqR;        // regrid partition of the tuned kernel
   int use_chain, rec_status;
   Chain ch;
 };
