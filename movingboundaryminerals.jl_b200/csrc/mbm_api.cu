@@ -125,11 +125,16 @@ int launch_v2_TN(const mbm::KArgs &A, int member0, int count, size_t smem_bytes,
 }
 template <int T>
 int launch_v2_T(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
+#ifdef MBM_DEV_MIN   // A/B builds: only the bench instantiation (T = 256, ndim = 2)
+  if (T == 256 && A.ndim == 2) return launch_v2_TN<256, 2>(A, member0, count, smem_bytes, s);
+  return MBM_RC_UNSUPPORTED;
+#else
   switch (A.ndim) {
     case 1: return launch_v2_TN<T, 1>(A, member0, count, smem_bytes, s);
     case 2: return launch_v2_TN<T, 2>(A, member0, count, smem_bytes, s);
     default: return launch_v2_TN<T, 3>(A, member0, count, smem_bytes, s);
   }
+#endif
 }
 
 template <int T, int NDIM>
@@ -141,11 +146,16 @@ int launch_fixed_TN(const mbm::KArgs &A, int member0, int count, size_t smem_byt
 }
 template <int T>
 int launch_fixed_T(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
+#ifdef MBM_DEV_MIN
+  if (T == 256 && A.ndim == 2) return launch_fixed_TN<256, 2>(A, member0, count, smem_bytes, s);
+  return MBM_RC_UNSUPPORTED;
+#else
   switch (A.ndim) {
     case 1: return launch_fixed_TN<T, 1>(A, member0, count, smem_bytes, s);
     case 2: return launch_fixed_TN<T, 2>(A, member0, count, smem_bytes, s);
     default: return launch_fixed_TN<T, 3>(A, member0, count, smem_bytes, s);
   }
+#endif
 }
 template <int NDIM>
 int launch_stream_N(const mbm::KArgs &A, int member0, int count, cudaStream_t s) {
@@ -153,11 +163,15 @@ int launch_stream_N(const mbm::KArgs &A, int member0, int count, cudaStream_t s)
   return launch_rc("streaming kernel launch", cudaGetLastError());
 }
 int launch_stream(const mbm::KArgs &A, int member0, int count, cudaStream_t s) {
+#ifdef MBM_DEV_MIN
+  return launch_stream_N<2>(A, member0, count, s);
+#else
   switch (A.ndim) {
     case 1: return launch_stream_N<1>(A, member0, count, s);
     case 2: return launch_stream_N<2>(A, member0, count, s);
     default: return launch_stream_N<3>(A, member0, count, s);
   }
+#endif
 }
 
 // static shared memory of one instantiation, asked from the runtime (an estimate that is a few KB short makes the
@@ -170,11 +184,15 @@ int static_smem_of(K kern) {
 }
 template <int T>
 int fixed_static_T(int ndim) {
+#ifdef MBM_DEV_MIN
+  return static_smem_of(mbm::mbm_fixed_kernel<256, 2>);
+#else
   switch (ndim) {
     case 1: return static_smem_of(mbm::mbm_fixed_kernel<T, 1>);
     case 2: return static_smem_of(mbm::mbm_fixed_kernel<T, 2>);
     default: return static_smem_of(mbm::mbm_fixed_kernel<T, 3>);
   }
+#endif
 }
 
 // fixed-interface kernel: nine arrays of kF doubles per member (n1 + n2 <= kF)
@@ -196,11 +214,15 @@ void fixed_plan(int capL, int capR, int nmax_hint, int smem_optin, int ndim, int
 // two CTAs per SM (four arrays of kS doubles) and one scan tile per thread and phase (9*T nodes per phase)
 template <int T>
 int v2_static_T(int ndim) {
+#ifdef MBM_DEV_MIN
+  return static_smem_of(mbm::mbm_step_kernel_v2<256, 2>);
+#else
   switch (ndim) {
     case 1: return static_smem_of(mbm::mbm_step_kernel_v2<T, 1>);
     case 2: return static_smem_of(mbm::mbm_step_kernel_v2<T, 2>);
     default: return static_smem_of(mbm::mbm_step_kernel_v2<T, 3>);
   }
+#endif
 }
 void v2_plan(int capL, int capR, int smem_per_sm, int ndim, int *T2, int *kS) {
   int ks = capL + capR + 1;
@@ -332,6 +354,13 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
       ++launches;
       A.only_deferred = 1;
     }
+#ifdef MBM_DEV_MIN
+    if (T != 256) return MBM_RC_UNSUPPORTED;
+    rc = launch_T<256>(A, m0 + off, n, use_global, dyn, s);
+    if (rc) return rc;
+    ++launches;
+    continue;
+#else
     switch (T) {
       case 32: rc = launch_T<32>(A, m0 + off, n, use_global, dyn, s); break;
       case 64: rc = launch_T<64>(A, m0 + off, n, use_global, dyn, s); break;
@@ -339,6 +368,7 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
       case 512: rc = launch_T<512>(A, m0 + off, n, use_global, dyn, s); break;
       default: rc = launch_T<256>(A, m0 + off, n, use_global, dyn, s); break;
     }
+#endif
     if (rc) return rc;
     ++launches;
   }
