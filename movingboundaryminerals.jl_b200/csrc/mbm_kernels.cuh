@@ -69,6 +69,7 @@ struct Scal {
   double cu0, cu1, cu2, cd0, cd1, cd2, CLB, CRB;
   double grid_d, grid_S, grid_total;
   double red[128];
+  double recbuf[16];                 // tuned kernel: the next step's record, staged by cp.async
   long long it, steps, node_steps, resmin1, resmin2;
   unsigned long long hash;
   int n1, n2, gap, nr1, nr2, Fl, status, warn, bc0, bc1, hidx, arrhenius;
