@@ -18,6 +18,14 @@
 
 namespace mbm {
 
+#ifndef MBM_SPF
+#define MBM_SPF 8
+#endif
+#ifndef MBM_STREAM_MINB
+#define MBM_STREAM_MINB 2
+#endif
+constexpr int SPF = MBM_SPF;   // software prefetch distance of the column sweeps, in rows (one row of a CTA = 2 KB per array)
+
 struct StreamLayout {
   int m;        // nodes per column
   int colR0;    // first column of the right phase
@@ -52,8 +60,137 @@ __device__ __forceinline__ double stream_slope(const double *X, const double *C,
   return slope_interior(fabs(ihm), fabs(ihp), (y0 - ym) * ihm, (yp - y0) * ihp);
 }
 
+// ---- regrid of one new column: the tuned kernel's interval-driven pchip walk (pchip_run, mbm_kernel_v2.cuh) over the
+// chunk-interleaved layout.  Old nodes are visited in phase order; thread t's new nodes fall into old column ~t, so
+// the walk of all threads is one coalesced stream with incremental addressing (no index divisions on the way).
+// Right phase (stored by reversed node index): the walk runs in mirrored coordinates x' = -x, which are
+// increasing in phase order; the interpolant is invariant and indices / branches are mapped back for the checksum.
+template <int T>
+__device__ __forceinline__ PPt spt(const double *X, const double *C, const StreamLayout &L, int phase, double sg, int i) {
+  const size_t a = paddr(T, L, phase, i);
+  PPt q; q.x = sg * X[a]; q.y = C[a];
+  return q;
+}
+// three-point end slope (functions.jl:786-806) at end node Pe with inward neighbours Pa, Pb (x increasing or decreasing)
+__device__ __noinline__ double end_slope3(PPt Pe, PPt Pa, PPt Pb) {
+  const double h1 = fabs(Pa.x - Pe.x), h2 = fabs(Pb.x - Pa.x);
+  const double sg = (Pa.x > Pe.x) ? 1.0 : -1.0;
+  const double m1 = sg * (Pa.y - Pe.y) * (1.0 / h1), m2 = sg * (Pb.y - Pa.y) * (1.0 / h2);
+  double d = fma(fma(2.0, h1, h2), m1, -(h1 * m2)) * (1.0 / (h1 + h2));
+  if (m1 * m2 < 0.0 || m1 == 0.0 || m2 == 0.0) d = 0.0;
+  return d;
+}
+
+template <int T>
+__device__ __forceinline__ void pchip_run_stream(const double *X, const double *C, const StreamLayout &L, const int phase,
+                                                 const int n, const int nn, const double lr_a, const double lr_b,
+                                                 double *Xn, double *Cn, const int idx0, const int cnt,
+                                                 const bool do_hash, const long long it, unsigned long long &hash) {
+  const int tid = threadIdx.x;
+  const bool MIR = (phase != 0);                      // runtime: both phases run one instruction stream
+  const double sg = MIR ? -1.0 : 1.0;
+  auto newx = [&](int pi) { return linrange_at(lr_a, lr_b, nn, MIR ? (nn - 1 - pi) : pi); };     // reference node order
+  auto emit = [&](int k, double xj, double val, int kk, int br) {
+    const size_t an = saddr(T, tid, k);
+    Xn[an] = xj; Cn[an] = val;
+    if (do_hash) {
+      if (MIR) {                                      // back to the reference's (forward) node order and branch names
+        if (br == 0) kk = n - 1 - kk;
+        else if (br == 1) { kk = 0; br = 2; }
+        else if (br == 2) { kk = n - 1; br = 1; }
+        else kk = n - 2 - kk;
+      }
+      hash += idx_term(it, phase, MIR ? (nn - 1 - (idx0 + k)) : (idx0 + k), kk, br);
+    }
+  };
+  double xj = newx(idx0);
+  double Xj = sg * xj;
+  // c = number of old nodes (phase order) strictly below the first new node, by walking from the proportional guess
+  int c = min(max((int)(((long long)idx0 * n) / nn), 1), n - 1);
+  {
+    double xa = spt<T>(X, C, L, phase, sg, c - 1).x, xb0 = spt<T>(X, C, L, phase, sg, c).x;
+    int steps = 0;
+    while (xb0 < Xj && c < n) {
+      ++c; xa = xb0; xb0 = (c < n) ? spt<T>(X, C, L, phase, sg, c).x : xb0;
+      if (++steps > 64) break;
+    }
+    while (!(xa < Xj) && c > 0 && steps <= 64) {
+      --c; xa = (c > 0) ? spt<T>(X, C, L, phase, sg, c - 1).x : xa;
+      ++steps;
+    }
+    if (steps > 64) {
+      int lo = 0, hi = n;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (spt<T>(X, C, L, phase, sg, mid).x < Xj) lo = mid + 1; else hi = mid; }
+      c = lo;
+    }
+  }
+  int j = 0;
+  while (c == 0) {                                    // at or below the first old node: branch 0 / 2
+    const PPt q0 = spt<T>(X, C, L, phase, sg, 0);
+    if (!(Xj <= q0.x)) { c = 1; break; }
+    emit(j, xj, q0.y, 0, (Xj == q0.x) ? 0 : 2);
+    if (++j == cnt) return;
+    xj = newx(idx0 + j); Xj = sg * xj;
+  }
+  int k = c - 1;                                      // current old interval [k, k+1]
+  if (k <= n - 2) {
+    PPt Q0 = spt<T>(X, C, L, phase, sg, k), Q1 = spt<T>(X, C, L, phase, sg, k + 1), Q2 = Q1, Q3 = Q1;
+    double IHa = frcp_(Q1.x - Q0.x), Ma = (Q1.y - Q0.y) * IHa, IHb = 0.0, Mb = 0.0, Da, Db;
+    if (k == 0) Da = end_slope3(Q0, Q1, spt<T>(X, C, L, phase, sg, 2));
+    else { const PPt Qm = spt<T>(X, C, L, phase, sg, k - 1); const double ihm = frcp_(Q0.x - Qm.x); Da = slope_interior(ihm, IHa, (Q0.y - Qm.y) * ihm, Ma); }
+    if (k + 1 == n - 1) Db = end_slope3(Q1, Q0, spt<T>(X, C, L, phase, sg, n - 3));
+    else { Q2 = spt<T>(X, C, L, phase, sg, k + 2); IHb = frcp_(Q2.x - Q1.x); Mb = (Q2.y - Q1.y) * IHb; Db = slope_interior(IHa, IHb, Ma, Mb); }
+    // sequential reader positioned at old index k + 3
+    int wrow = 0; size_t wa = 0;
+    if (k + 3 <= n - 1) { const int i3 = k + 3; wrow = i3 % L.m; wa = (size_t)wrow * T + (size_t)((phase ? L.colR0 : 0) + i3 / L.m); }
+#define MBM_SSTEP(P0, P1, P2, P3, IH0, M0, D0, IH1, M1, D1)                                                   \
+    {                                                                                                          \
+      const double h = P1.x - P0.x;                                                                            \
+      while (Xj <= P1.x) {                                                                                     \
+        const double sx = Xj - P0.x;                                                                           \
+        const double u = sx * IH0, smh = sx - h;                                                               \
+        const double u2 = u * u;                                                                               \
+        const double w2 = u2 * (3.0 - 2.0 * u);                                                                \
+        double val = w2 * P1.y + (1.0 - w2) * P0.y + (u2 * smh) * D1 + (u * smh) * (smh * IH0) * D0;           \
+        const bool eq = (Xj == P1.x);                                                                          \
+        if (eq) val = P1.y;                                                                                    \
+        emit(j, xj, val, eq ? k + 1 : k, eq ? 0 : 3);                                                          \
+        if (++j == cnt) return;                                                                                \
+        xj = newx(idx0 + j); Xj = sg * xj;                                                              \
+      }                                                                                                        \
+      if (k + 3 <= n - 1) {                                                                                    \
+        if (wrow + SPF < L.m) {                                                                                \
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(X + wa + (size_t)SPF * T));                            \
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(C + wa + (size_t)SPF * T));                            \
+        }                                                                                                      \
+        P3.x = sg * X[wa]; P3.y = C[wa];                                                             \
+        if (++wrow == L.m) { wrow = 0; wa = wa + 1 - (size_t)(L.m - 1) * T; } else wa += T;                    \
+        IH0 = frcp_(P3.x - P2.x); M0 = (P3.y - P2.y) * IH0;                                                    \
+        D0 = slope_interior(IH1, IH0, M1, M0);                                                                 \
+      } else if (k + 3 == n) D0 = end_slope3(P2, P1, P0);                                                      \
+      else break;                                                                                              \
+      ++k;                                                                                                     \
+    }
+    for (;;) {
+      MBM_SSTEP(Q0, Q1, Q2, Q3, IHa, Ma, Da, IHb, Mb, Db)
+      MBM_SSTEP(Q1, Q2, Q3, Q0, IHb, Mb, Db, IHa, Ma, Da)
+      MBM_SSTEP(Q2, Q3, Q0, Q1, IHa, Ma, Da, IHb, Mb, Db)
+      MBM_SSTEP(Q3, Q0, Q1, Q2, IHb, Mb, Db, IHa, Ma, Da)
+    }
+#undef MBM_SSTEP
+  }
+  {                                                   // above the last old node: branch 1
+    const double yl = spt<T>(X, C, L, phase, sg, n - 1).y;
+    for (;;) {
+      emit(j, xj, yl, n - 1, 1);
+      if (++j == cnt) return;
+      xj = newx(idx0 + j);
+    }
+  }
+}
+
 template <int T, int NDIM>
-__global__ void __launch_bounds__(T, 2) mbm_stream_kernel(const KArgs A, const int member0) {
+__global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream_kernel(const KArgs A, const int member0) {
   __shared__ Scal S;
   __shared__ double redS[T], redD[T], redU[T], red0[T], red1[T];
   __shared__ double exA[T], exG[T], exR[T];
@@ -242,62 +379,61 @@ __global__ void __launch_bounds__(T, 2) mbm_stream_kernel(const KArgs A, const i
     }
     __syncthreads();
     if (active) {
-      // forward sweep over the column (coalesced: element k of column t at k*T + t)
-      const int SDp = blk ? -1 : 1;        // orientation of x along the sweep: left increasing, right (reversed) decreasing
-      double x_self = X[saddr(T, tid, 0)], c_self = C[saddr(T, tid, 0)];
-      double x_prev = x_halo_prev, c_prev = c_halo_prev;
-      double pAc = 0.0, pAnext = 0.0, pkk = 0.0;
-      const bool haveP0 = f > 0;
-      if (haveP0) {
-        double A11, A12, A22, kk;
-        if (SDp > 0) elem_mats_fast<NDIM>(x_prev, x_self, Dph, idt, A11, A12, A22, kk);
-        else elem_mats_fast<NDIM>(x_self, x_prev, Dph, idt, A11, A12, A22, kk);
-        pAnext = (SDp > 0) ? A22 : A11; pAc = A12; pkk = kk;
+      // forward sweep over the column (coalesced: element k of column t at k*T + t), same row arithmetic as the tuned
+      // resident kernel (direction-agnostic element matrices, combined element carry).  The first row of the column
+      // in terms of the two separators, C_0 = bR - bA*s_prev - bG*s_own, is accumulated on the way
+      // (bR = sum pi_k R_k, bA = sum pi_k A_k, pi_k = prod_{j<k}(-G_j), bG = -pi_{len-1}): no second pass over A, G, R.
+      const int sd = blk ? -1 : 1;         // orientation of x along the sweep: left increasing, right (reversed) decreasing
+      const double Dsd = (sd > 0) ? Dph : -Dph, idts = (sd > 0) ? idt : -idt;
+      size_t a = saddr(T, tid, 0);
+      double x_self = X[a], c_self = C[a];
+      double dcar = 0.0, rcar = 0.0, sub = 0.0, hprev = 0.0, Vs = 0.0, Qb = 0.0, pi = 1.0;
+      if (mb) Vs = powd<NDIM>(x_self);
+      if (f > 0) {
+        double Apv, A12, Aown, kk;
+        elem_mats_dir<NDIM>(x_halo_prev, x_self, Dsd, idts, Apv, A12, Aown, kk);
+        dcar = Aown - kk; rcar = fma(A12, c_halo_prev, Aown * c_self); sub = A12 + kk;
+        if (mb) hprev = 0.5 * fabs(Vs - powd<NDIM>(x_halo_prev));
       }
-      double Qb = 0.0, Vs = 0.0, Vm = 0.0;
-      if (mb) { Vs = powd<NDIM>(x_self); Vm = haveP0 ? powd<NDIM>(x_prev) : Vs; }
-      double xn_pf = (len > 1) ? X[saddr(T, tid, 1)] : x_halo_next, cn_pf = (len > 1) ? C[saddr(T, tid, 1)] : c_halo_next;
-#pragma unroll 1
-      for (int k = 0; k < len; ++k) {
-        const double x_next = xn_pf, c_next = cn_pf;
-        if (k + 2 < len) { xn_pf = X[saddr(T, tid, k + 2)]; cn_pf = C[saddr(T, tid, k + 2)]; }   // prefetch one row ahead
-        else { xn_pf = x_halo_next; cn_pf = c_halo_next; }
-        double A11, A12, A22, kk;
-        if (SDp > 0) elem_mats_fast<NDIM>(x_self, x_next, Dph, idt, A11, A12, A22, kk);
-        else elem_mats_fast<NDIM>(x_next, x_self, Dph, idt, A11, A12, A22, kk);
-        const double nAself = (SDp > 0) ? A11 : A22, nAnext = (SDp > 0) ? A22 : A11;
-        double diag = (nAself - kk) + (pAnext - pkk);
-        double rhs = (nAself * c_self + A12 * c_next) + (pAc * c_prev + pAnext * c_self);
-        double sup = A12 + kk, sub = pAc + pkk;
-        if (dir0 && k == 0) { diag = 1.0; rhs = Co_out; sup = 0.0; sub = 0.0; }
+      bA = 0.0; bR = 0.0;
+      for (int d = 1; d < SPF && d < len; ++d) {                         // warm the first rows
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(X + a + (size_t)d * T));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(C + a + (size_t)d * T));
+      }
+#pragma unroll 2
+      for (int k = 0; k < len; ++k, a += T) {
+        const bool last = (k == len - 1);
+        if (k + SPF < len) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(X + a + (size_t)SPF * T));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(C + a + (size_t)SPF * T));
+        }
+        const double x_next = last ? x_halo_next : X[a + T], c_next = last ? c_halo_next : C[a + T];
+        double Aself, A12, Anext, kk;
+        elem_mats_dir<NDIM>(x_self, x_next, Dsd, idts, Aself, A12, Anext, kk);
+        double diag = (Aself - kk) + dcar;
+        double rhs = fma(Aself, c_self, A12 * c_next) + rcar;
+        const double sup_true = A12 + kk;
+        double sup = sup_true;
+        if (k == 0 && dir0) { diag = 1.0; rhs = Co_out; sup = 0.0; sub = 0.0; }
         const double inv = frcp_(diag - sub * Gp);
         const double An = (k == 0) ? (sub * inv) : (-sub * Ap * inv);
         const double Gn = sup * inv;
         const double Rn = (rhs - sub * Rp) * inv;
-        const size_t a = saddr(T, tid, k);
         FA[a] = An; FG[a] = Gn; C[a] = Rn;
+        if (!last) { bR = fma(pi, Rn, bR); bA = fma(pi, An, bA); pi = -pi * Gn; }
         if (mb) {
           const double Vn = powd<NDIM>(x_next);
-          const double wgt = 0.5 * fabs(Vn - Vs) + 0.5 * fabs(Vs - Vm);
-          if (k < len - 1) { const double tq = Qb + wgt; P0 = fma(tq, Rn, P0); Qa = fma(-tq, An, Qa); Qb = -tq * Gn; }
+          const double hn = 0.5 * fabs(Vn - Vs);
+          const double wgt = hn + hprev;
+          if (!last) { const double tq = Qb + wgt; P0 = fma(tq, Rn, P0); Qa = fma(-tq, An, Qa); Qb = -tq * Gn; }
           else Qc = Qb + wgt;
-          Vm = Vs; Vs = Vn;
+          Vs = Vn; hprev = hn;
         }
         Ap = An; Gp = Gn; Rp = Rn;
-        x_prev = x_self; c_prev = c_self; x_self = x_next; c_self = c_next;
-        pAc = A12; pAnext = nAnext; pkk = kk;
+        dcar = Anext - kk; rcar = fma(A12, c_self, Anext * c_next); sub = sup_true;
+        x_self = x_next; c_self = c_next;
       }
-      // backward accumulation (division-free): first row of the column in terms of the two separators
-      if (len > 1) {
-        size_t a = saddr(T, tid, len - 2);
-        bA = FA[a]; bG = FG[a]; bR = C[a];
-#pragma unroll 1
-        for (int k = len - 3; k >= 0; --k) {
-          a -= T;
-          const double Gk = FG[a];
-          bR = C[a] - Gk * bR; bA = FA[a] - Gk * bA; bG = -Gk * bG;
-        }
-      }
+      bG = -pi;
     }
     exA[tid] = bA; exG[tid] = bG; exR[tid] = bR;
     __syncthreads();
@@ -347,7 +483,15 @@ __global__ void __launch_bounds__(T, 2) mbm_stream_kernel(const KArgs A, const i
       size_t a = saddr(T, tid, len - 1);
       C[a] = cn;
 #pragma unroll 2
-      for (int k = len - 2; k >= 0; --k) { a -= T; cn = C[a] - FA[a] * sp - FG[a] * cn; C[a] = cn; }
+      for (int k = len - 2; k >= 0; --k) {
+        a -= T;
+        if (k >= SPF) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(C + a - (size_t)SPF * T));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(FA + a - (size_t)SPF * T));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(FG + a - (size_t)SPF * T));
+        }
+        cn = C[a] - FA[a] * sp - FG[a] * cn; C[a] = cn;
+      }
     }
     if (tid == 0) { C[paddr(T, L, 0, n1 - 1)] = aif; C[paddr(T, L, 1, n2 - 1)] = bif; }
     __threadfence_block();
@@ -365,66 +509,8 @@ __global__ void __launch_bounds__(T, 2) mbm_stream_kernel(const KArgs A, const i
       const int no = nblk ? n2 : n1;            // old node count of the phase
       const int idx0 = ncol * LN.m;
       const int cnt = max(0, min(idx0 + LN.m, nn) - idx0);
-      int c = -1;                               // phase-ordered count of old nodes "before" the new node
-      double xa = 0.0, xb = 0.0;                // old nodes c-1 and c (phase order)
-      for (int k = 0; k < cnt; ++k) {
-        const int pi = idx0 + k;                                  // phase-ordered index of the new node
-        const int j = nblk ? (nn - 1 - pi) : pi;                  // node index in the reference's order
-        const double Xj = nblk ? linrange_at(Ri1, Ri2, nn, j) : linrange_at(0.0, Ri1, nn, j);
-        // walk in phase order.  Left: c = #old nodes with x < Xj.  Right (reversed order, x decreasing with index):
-        // c = #old nodes with x > Xj, i.e. the first old index whose x is <= Xj.
-        if (c < 0) {
-          c = min(max((int)(((long long)pi * no) / nn), 1), no - 1);
-          xa = X[paddr(T, L, nblk, c - 1)]; xb = X[paddr(T, L, nblk, c)];
-        }
-        int steps = 0;
-        if (!nblk) {
-          while (c < no && xb < Xj) { ++c; xa = xb; xb = (c < no) ? X[paddr(T, L, 0, c)] : xb; if (++steps > 64) break; }
-          while (c > 0 && !(xa < Xj) && steps <= 64) { --c; xb = xa; xa = (c > 0) ? X[paddr(T, L, 0, c - 1)] : xa; ++steps; }
-          if (steps > 64) {
-            int lo = 0, hi = no;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (X[paddr(T, L, 0, mid)] < Xj) lo = mid + 1; else hi = mid; }
-            c = lo; xa = (c > 0) ? X[paddr(T, L, 0, c - 1)] : 0.0; xb = (c < no) ? X[paddr(T, L, 0, c)] : 0.0;
-          }
-        } else {
-          while (c < no && xb > Xj) { ++c; xa = xb; xb = (c < no) ? X[paddr(T, L, 1, c)] : xb; if (++steps > 64) break; }
-          while (c > 0 && !(xa > Xj) && steps <= 64) { --c; xb = xa; xa = (c > 0) ? X[paddr(T, L, 1, c - 1)] : xa; ++steps; }
-          if (steps > 64) {
-            int lo = 0, hi = no;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (X[paddr(T, L, 1, mid)] > Xj) lo = mid + 1; else hi = mid; }
-            c = lo; xa = (c > 0) ? X[paddr(T, L, 1, c - 1)] : 0.0; xb = (c < no) ? X[paddr(T, L, 1, c)] : 0.0;
-          }
-        }
-        // reference semantics (functions.jl:809-837) in the reference's node order (fwd index = no-1-idx for the right phase)
-        double Pj; int kk, br;
-        if (!nblk) {
-          if (c < no && xb == Xj) { kk = c; br = 0; Pj = C[paddr(T, L, 0, c)]; }
-          else if (c == no) { kk = no - 1; br = 1; Pj = C[paddr(T, L, 0, no - 1)]; }
-          else if (c == 0) { kk = 0; br = 2; Pj = C[paddr(T, L, 0, 0)]; }
-          else {
-            kk = c - 1; br = 3;
-            const double y1 = C[paddr(T, L, 0, c - 1)], y2 = C[paddr(T, L, 0, c)];
-            const double d1 = stream_slope<T>(X, C, L, 0, no, c - 1), d2 = stream_slope<T>(X, C, L, 0, no, c);
-            const double h = xb - xa, ih = frcp_(h), s = Xj - xa, u = s * ih, smh = s - h, u2 = u * u, w2 = u2 * (3.0 - 2.0 * u);
-            Pj = w2 * y2 + (1.0 - w2) * y1 + (u2 * smh) * d2 + (u * smh) * (smh * ih) * d1;
-          }
-        } else {
-          // reversed phase: old idx c-1 has x = xa > Xj >= xb = x of idx c (or c == no: Xj below all; c == 0: above all)
-          if (c < no && xb == Xj) { kk = no - 1 - c; br = 0; Pj = C[paddr(T, L, 1, c)]; }
-          else if (c > 0 && xa == Xj) { kk = no - c; br = 0; Pj = C[paddr(T, L, 1, c - 1)]; }
-          else if (c == 0) { kk = no - 1; br = 1; Pj = C[paddr(T, L, 1, 0)]; }                   // X > max(x): value at the max
-          else if (c == no) { kk = 0; br = 2; Pj = C[paddr(T, L, 1, no - 1)]; }                   // X < min(x)
-          else {
-            kk = no - 1 - c; br = 3;                                                              // fwd interval [x_fwd[kk], x_fwd[kk+1]] = [xb, xa]
-            const double y1 = C[paddr(T, L, 1, c)], y2 = C[paddr(T, L, 1, c - 1)];
-            const double d1 = stream_slope<T>(X, C, L, 1, no, c), d2 = stream_slope<T>(X, C, L, 1, no, c - 1);
-            const double h = xa - xb, ih = frcp_(h), s = Xj - xb, u = s * ih, smh = s - h, u2 = u * u, w2 = u2 * (3.0 - 2.0 * u);
-            Pj = w2 * y2 + (1.0 - w2) * y1 + (u2 * smh) * d2 + (u * smh) * (smh * ih) * d1;
-          }
-        }
-        const size_t an = saddr(T, tid, k);
-        Xn[an] = Xj; Cn[an] = Pj;
-        if (do_hash) hash_local += idx_term(S.it, nblk, j, kk, br);
+      if (cnt > 0) {
+        pchip_run_stream<T>(X, C, L, nblk, no, nn, nblk ? Ri1 : 0.0, nblk ? Ri2 : Ri1, Xn, Cn, idx0, cnt, do_hash, S.it, hash_local);
       }
     }
     __threadfence_block();
