@@ -32,8 +32,10 @@ __device__ __noinline__ double jl_pow_int(double x, long long n) {
     x = rx;
     n = -n;
   }
-  while (n > 1) {
-    if (n & 1) {
+  int m = (int)n;                      // node counts: 32-bit loop control (n < 2^31 is guaranteed by the capacities)
+  if (n > 0x7fffffffll) m = 0x7fffffff;
+  while (m > 1) {
+    if (m & 1) {
       double err = fma(y, xnlo, xmul(x, ynlo));
       double hi = xmul(x, y);
       double lo = fma(x, y, -hi);
@@ -45,7 +47,7 @@ __device__ __noinline__ double jl_pow_int(double x, long long n) {
     double lo2 = fma(x, x, -hi2);
     x = hi2;
     xnlo = xadd(lo2, err2);
-    n >>= 1;
+    m >>= 1;
   }
   double err = fma(y, xnlo, xmul(x, ynlo));
   if (isfinite(x) && isfinite(err)) return fma(x, y, err);

@@ -105,6 +105,21 @@ __device__ __forceinline__ void block_sum4(double v[4], double *scratch) {
   }
 }
 
+// block-wide sum of 2 values (the tuned kernel's mass-balance row); result broadcast to all threads
+template <int T>
+__device__ __forceinline__ void block_sum2(double v[2], double *scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v[0] = warp_sum(v[0]); v[1] = warp_sum(v[1]);
+  if (T == 32) return;
+  cta_sync<T>();
+  if (lane == 0) { scratch[w * 2] = v[0]; scratch[w * 2 + 1] = v[1]; }
+  cta_sync<T>();
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int ww = 0; ww < T / 32; ++ww) { s0 += scratch[ww * 2]; s1 += scratch[ww * 2 + 1]; }
+  v[0] = s0; v[1] = s1;
+}
+
 // ---- canonical scan (tiles of 9, Hillis-Steele over 32 tiles, sequential over groups) ---------------
 // Computes the inclusive scan of gen(i), i = 0..n-1, into out[0..n-1] (shared or global memory).
 // OP = 0: sum, 1: product.  gtot: scratch for group totals (>= ceil(n/288) doubles).  All threads call.
@@ -493,15 +508,18 @@ __device__ __forceinline__ double pchip_eval_one(const double *x, const double *
 __device__ __forceinline__ double frcp_(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  r = fma(fma(-x, r, 1.0), r, r);
-  r = fma(fma(-x, r, 1.0), r, r);
-  return r;
+  // seed error e ~ 2^-20: r (1 + e + e^2) leaves e^3 ~ 2^-60, one dependent FMA less than two Newton steps
+  const double e = fma(-x, r, 1.0);
+  return fma(fma(e, e, e), r, r);
 }
 __device__ __forceinline__ double slope_interior(double ihm, double ihp, double mm, double mp) {
   // d = (w- m- + w+ m+)/(w- + w+), w = 2/h (the factor 2 cancels); zero on sign change / zero secant; limiter 3*min|m|
   const double d = (ihm * mm + ihp * mp) * frcp_(ihm + ihp);
-  const double lim = 3.0 * fmin(fabs(mm), fabs(mp));
-  const double ad = (mm * mp > 0.0) ? fmin(fabs(d), lim) : 0.0;
+  // plain compare-selects (fmin's NaN handling costs five extra instructions each; a NaN profile is status 11 anyway)
+  const double am = fabs(mm), ap = fabs(mp), a0 = fabs(d);
+  const double lim = 3.0 * ((am < ap) ? am : ap);
+  double ad = (a0 < lim) ? a0 : lim;
+  ad = (mm * mp > 0.0) ? ad : 0.0;
   return copysign(ad, d);
 }
 // pchip evaluation of one new node with the two slopes of its interval computed on the fly
