@@ -32,6 +32,7 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
+TRAFFIC_BYTES_8192 = 485.8e6 + 590.6e6     # ncu, see roofline.traffic below
 sys.path.insert(0, str(ROOT))
 
 
@@ -44,7 +45,8 @@ def parse():
     ap.add_argument("--members-per-gpu", type=int, default=int(os.environ.get("MBM_BENCH_MEMBERS", 8192)))
     ap.add_argument("--res", type=int, default=1024)
     ap.add_argument("--tsteps", type=int, default=int(os.environ.get("MBM_BENCH_TSTEPS", 250)))
-    ap.add_argument("--cpu-members", type=int, default=64)
+    ap.add_argument("--cpu-members", type=int, default=1024)
+    ap.add_argument("--cpu-tsteps", type=int, default=1000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -299,10 +301,13 @@ def main():
         pass
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     roofline = {"bound": "fp64", "achieved": per_gpu * flops_per_ns * 1e-12, "peak": dfma, "unit": "TFLOP/s",
-                "frac": (per_gpu * flops_per_ns * 1e-12 / dfma) if dfma > 0 else None, "traffic": None,
+                "frac": (per_gpu * flops_per_ns * 1e-12 / dfma) if dfma > 0 else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload (8192 members x 250 time steps),
+                # `ncu --set full` capture summarised in profiles/r01_ncu_v2kernel_head_summary.txt; scaled with the members
+                "traffic": TRAFFIC_BYTES_8192 * args.members_per_gpu / 8192.0,
                 "peak_source": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "flops_per_node_step": flops_per_ns, "kernel": "mbm_step_kernel_v2<256,2>", "kernel_ms_per_launch": kernel_ms,
-                "traffic_note": "ncu --set full on a 592-member launch (profiles/): dram read 37.5 MB + write 1.0 MB during the profiled window = state + histories in, once per launch; DRAM throughput 0.1 % of peak",
+                "traffic_note": "bytes per launch from ncu (486 MB read + 591 MB written at 8192 members): the state and the histories cross HBM once per launch, not once per step (0.16 % of DRAM throughput); algorithmic streaming traffic would be 32 B x node-steps = 157 GB per launch",
                 "hbm_view": {"bound": "hbm", "achieved": per_gpu * 32 * 1e-9, "peak": hbm, "unit": "GB/s",
                              "frac": per_gpu * 32 * 1e-9 / hbm, "bytes_per_node_step": 32,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
@@ -319,11 +324,11 @@ def main():
         ce.run(ora, max_steps=2)
         n0 = int(ce.node_steps.sum())
         t0 = time.perf_counter()
-        ce.run(ora, max_steps=args.tsteps)
+        ce.run(ora, max_steps=args.cpu_tsteps)
         tc = time.perf_counter() - t0
         cpu = {"value": (int(ce.node_steps.sum()) - n0) / tc, "unit": "node-steps/s", "cores": os.cpu_count(),
                "kind": "port",
-               "sample": f"{args.cpu_members} members x {args.tsteps} time steps of the same ensemble, structured O(N) solve, "
+               "sample": f"{args.cpu_members} members x {args.cpu_tsteps} time steps of the same ensemble, structured O(N) solve, "
                          f"OpenMP schedule(dynamic) over members, {tc:.1f} s"}
 
     line = {

@@ -355,7 +355,6 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
       A.only_deferred = 1;
     }
 #ifdef MBM_DEV_MIN
-    if (T != 256) return MBM_RC_UNSUPPORTED;
     rc = launch_T<256>(A, m0 + off, n, use_global, dyn, s);
     if (rc) return rc;
     ++launches;

@@ -341,7 +341,9 @@ __device__ __forceinline__ void hist_load(HistCache &h, const MemberPtrs &P, int
   h.k0 = P.KD_ar[i]; h.k1 = P.KD_ar[i + 1]; h.T0 = P.T_ar[i]; h.T1 = P.T_ar[i + 1];
 }
 // update_t_dependent_param! for the chain: same arithmetic as lin_interp_cursor / update_t_dependent
-__device__ inline int chain_update_params(const Scal &S, const KArgs &A, const MemberPtrs &P, double t, HistCache &h,
+// (SE: Scal, or chain_build's register copy of the fields read here)
+template <class SE>
+__device__ inline int chain_update_params(const SE &S, const KArgs &A, const MemberPtrs &P, double t, HistCache &h,
                                           double *KD, double *Tt, double *D_l, double *D_r) {
   if (t < S.tmin || t > S.tmax) return 6;
   if (t > h.x1 || t < h.x0 || (t == h.x0 && h.i > 0)) {          // left the cached interval: walk the cursor
@@ -375,21 +377,35 @@ __device__ inline int chain_update_params(const Scal &S, const KArgs &A, const M
 // Same operations, in the same order, as step_scalars + the closed-form mesh scalars of define_new_grid.
 // capL/capR: array capacities (exceeding them is the hard status 10); capS / capPhase: capacity of the calling
 // kernel's shared-memory layout (exceeding them is the soft code 13: the member is handed to the general kernel)
-__device__ inline void chain_build(Scal &S, const KArgs &A, const MemberPtrs &P, double *recs, int maxrec, int capL,
+// The chain state and the member constants it reads are copied to registers for the run (the records go to global
+// memory through a generic pointer, so the compiler would otherwise re-read every shared scalar after each store).
+struct ChainEnv {
+  double t_tot, CFL, Ri2, V, tmin, tmax, KDmin, KDmax, Tmin, Tmax, D00, D01, Ea0, Ea1, R, Di0, Di1;
+  long long resmin1, resmin2;
+  int arrhenius;
+};
+__device__ inline void chain_build(Scal &Sh, const KArgs &A, const MemberPtrs &P, double *recs, int maxrec, int capL,
                                    int capR, int capS, int capPhase) {
-  Chain &c = S.ch;
+  ChainEnv S;
+  S.t_tot = Sh.t_tot; S.CFL = Sh.CFL; S.Ri2 = Sh.Ri2; S.V = Sh.V; S.tmin = Sh.tmin; S.tmax = Sh.tmax;
+  S.KDmin = Sh.KDmin; S.KDmax = Sh.KDmax; S.Tmin = Sh.Tmin; S.Tmax = Sh.Tmax; S.D00 = Sh.D00; S.D01 = Sh.D01;
+  S.Ea0 = Sh.Ea0; S.Ea1 = Sh.Ea1; S.R = Sh.R; S.Di0 = Sh.Di0; S.Di1 = Sh.Di1;
+  S.resmin1 = Sh.resmin1; S.resmin2 = Sh.resmin2; S.arrhenius = Sh.arrhenius;
+  Chain c = Sh.ch;
   c.count = 0; c.pos = 0;
   const double V = S.V;
   const double iabsV = xinv(fabs(V));                 // loop invariants: same value every step, so hoisting is exact
   const double isum = xinv(c.csA);
   double mxD_c = fmax(c.D_l, c.D_r), imxD = xinv(mxD_c);
+  const int dt_mode = A.dt_mode;
+  const long long max_steps = A.max_steps;
   HistCache h;
   hist_load(h, P, c.hidx);
   while (c.count < maxrec) {
-    if (c.status != 0 || !(c.t < S.t_tot) || (A.max_steps > 0 && c.steps >= A.max_steps)) { c.done = 1; break; }
+    if (c.status != 0 || !(c.t < S.t_tot) || (max_steps > 0 && c.steps >= max_steps)) { c.done = 1; break; }
     // ---- dt (find_dt functions.jl:465-490 / C1.jl:93) and update_time! (:1442-1450)
     double dt;
-    if (A.dt_mode == DT_ADV) dt = xmul(xdiv(fmin(c.dx1, c.dx2), V), S.CFL);
+    if (dt_mode == DT_ADV) dt = xmul(xdiv(fmin(c.dx1, c.dx2), V), S.CFL);
     else {
       const double mn = fmin(c.dx1, c.dx2), mxD = fmax(c.D_l, c.D_r);
       if (mxD != mxD_c) { mxD_c = mxD; imxD = xinv(mxD); }
@@ -432,10 +448,14 @@ __device__ inline void chain_build(Scal &S, const KArgs &A, const MemberPtrs &P,
       c.need_scan = 1; c.scan_nl = (int)nr1 - 1;
       break;
     }
+    // ---- closed-form mesh scalars of define_new_grid (:402-410) from the cached scan totals
+    const double xl_last = xmul(xmul(c.csA, Rnew), isum);      // X_left[nr1-1]
+    const double xl_m2 = xmul(xmul(c.csB, Rnew), isum);        // X_left[nr1-2]
+    const double d = xsub(xl_last, xl_m2);
     double *r = recs + (size_t)c.count * REC_N;
     r[REC_DT] = dt; r[REC_T] = t; r[REC_KD] = KD; r[REC_TEMP] = Tt; r[REC_DL] = D_l; r[REC_DR] = D_r;
     r[REC_RI1] = Rnew; r[REC_NR1] = (double)nr1; r[REC_NR2] = (double)nr2; r[REC_STATUS] = (double)rc;
-    r[REC_WARN] = 0.0; r[REC_IT] = (double)(c.it + 1); r[REC_D] = 0.0; r[REC_R] = 0.0;
+    r[REC_WARN] = 0.0; r[REC_IT] = (double)(c.it + 1); r[REC_D] = rc ? 0.0 : d; r[REC_R] = 0.0;
     c.count += 1;
     c.steps += 1;
     c.it += 1;
@@ -443,17 +463,13 @@ __device__ inline void chain_build(Scal &S, const KArgs &A, const MemberPtrs &P,
     if (rc) { c.status = rc; c.done = 1; break; }
     c.D_l = D_l; c.D_r = D_r;
     c.Ri1 = Rnew;
-    // ---- closed-form mesh scalars of define_new_grid (:402-410) from the cached scan totals
-    const double xl_last = xmul(xmul(c.csA, Rnew), isum);      // X_left[nr1-1]
-    const double xl_m2 = xmul(xmul(c.csB, Rnew), isum);        // X_left[nr1-2]
-    const double d = xsub(xl_last, xl_m2);
-    r[REC_D] = d;
     c.xl_m2 = xl_m2;
     c.xr_1 = xadd(Rnew, d);                                    // X_right[1] = Ri1 + dx_right[0]
     c.dx1 = d;                                                 // regrid! :893
     c.dx2 = xsub(c.xr_1, Rnew);                                // :894
     c.n1 = (int)nr1; c.n2 = (int)nr2;
   }
+  Sh.ch = c;
 }
 
 // ---- pchip slope at node i of one phase (functions.jl:786-806; value code, contraction allowed) ------

@@ -74,7 +74,7 @@ def main():
         res.append(run("c5: MB growth n=65536/phase MRefin=1 (global-memory variant)",
                        lambda M: E.c5_highres(M, 65536, max_steps=100),
                        lambda lib, P: d.build_couple_ensemble(P, lib, cap_left=65540, cap_right=65540)[0],
-                       64, 20, 1, tol=1e-9))
+                       296, 20, 1, tol=1e-9))
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "configs.json").write_text(json.dumps(res, indent=1))
 
