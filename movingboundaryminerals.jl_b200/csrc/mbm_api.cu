@@ -116,6 +116,9 @@ int launch_T(const mbm::KArgs &A, int member0, int count, bool use_global, size_
   return launch_rc("general kernel launch", cudaGetLastError());
 }
 
+#ifndef MBM_V2_T
+#define MBM_V2_T 256
+#endif
 template <int T, int NDIM>
 int launch_v2_TN(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
   auto kern = mbm::mbm_step_kernel_v2<T, NDIM>;
@@ -125,8 +128,8 @@ int launch_v2_TN(const mbm::KArgs &A, int member0, int count, size_t smem_bytes,
 }
 template <int T>
 int launch_v2_T(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
-#ifdef MBM_DEV_MIN   // A/B builds: only the bench instantiation (T = 256, ndim = 2)
-  if (T == 256 && A.ndim == 2) return launch_v2_TN<256, 2>(A, member0, count, smem_bytes, s);
+#ifdef MBM_DEV_MIN   // A/B builds: only the bench instantiation (T = 256 unless MBM_V2_T says otherwise, ndim = 2)
+  if (T == 256 && A.ndim == 2) return launch_v2_TN<MBM_V2_T, 2>(A, member0, count, smem_bytes, s);
   return MBM_RC_UNSUPPORTED;
 #else
   switch (A.ndim) {
@@ -215,7 +218,7 @@ void fixed_plan(int capL, int capR, int nmax_hint, int smem_optin, int ndim, int
 template <int T>
 int v2_static_T(int ndim) {
 #ifdef MBM_DEV_MIN
-  return static_smem_of(mbm::mbm_step_kernel_v2<256, 2>);
+  return static_smem_of(mbm::mbm_step_kernel_v2<MBM_V2_T, 2>);
 #else
   switch (ndim) {
     case 1: return static_smem_of(mbm::mbm_step_kernel_v2<T, 1>);
@@ -239,6 +242,9 @@ void v2_plan(int capL, int capR, int smem_per_sm, int ndim, int *T2, int *kS) {
     const int t = atoi(e);
     if (t == 64 || t == 128 || t == 256) T = t;
   }
+#if defined(MBM_DEV_MIN) && MBM_V2_T != 256
+  if (T == 256) { *T2 = MBM_V2_T; *kS = ks; return; }      // the launch switch maps "256" to the MBM_V2_T instantiation
+#endif
   *T2 = T; *kS = ks;
 }
 
