@@ -531,12 +531,13 @@ __device__ __forceinline__ double frcp_(double x) {
 __device__ __forceinline__ double slope_interior(double ihm, double ihp, double mm, double mp) {
   // d = (w- m- + w+ m+)/(w- + w+), w = 2/h (the factor 2 cancels); zero on sign change / zero secant; limiter 3*min|m|
   const double d = (ihm * mm + ihp * mp) * frcp_(ihm + ihp);
-  // plain compare-selects (fmin's NaN handling costs five extra instructions each; a NaN profile is status 11 anyway)
-  const double am = fabs(mm), ap = fabs(mp), a0 = fabs(d);
-  const double lim = 3.0 * ((am < ap) ? am : ap);
-  double ad = (a0 < lim) ? a0 : lim;
-  ad = (mm * mp > 0.0) ? ad : 0.0;
-  return copysign(ad, d);
+  // compare magnitudes, select SIGNED values: with mm*mp > 0 the mean d and both secants share one sign, so the
+  // limited slope is d or 3*(the secant of smaller magnitude) as it stands - no fabs values to materialise, no copysign
+  // (fmin would add NaN handling on top; a NaN profile is status 11 anyway)
+  const double mn = (fabs(mm) < fabs(mp)) ? mm : mp;
+  const double lim = 3.0 * mn;
+  const double r = (fabs(d) < fabs(lim)) ? d : lim;
+  return (mm * mp > 0.0) ? r : 0.0;
 }
 // pchip evaluation of one new node with the two slopes of its interval computed on the fly
 // (functions.jl:786-837: same slopes, same branch/index semantics; no slope array needed)
