@@ -70,26 +70,19 @@ __device__ __noinline__ double linrange_at(double a, double b, long long len, lo
 // x^n and x^(n-1) in one pass: the two pow_body calls of a Newton iteration square the same x, so the (x, xnlo)
 // sequence is computed once and only the two y accumulations differ.  Every operation of either call is executed
 // with the same operands in the same order as in jl_pow_int, so both results are bit-identical to separate calls.
-// Requires 4 < n < 2^31 (smaller exponents take pow_body's special cases: use jl_pow_int).
+// Requires 4 < n < 2^31 and n not a power of two (then n and n-1 have the same bit length and both loops run the same
+// number of rounds); other exponents use jl_pow_int (pow_body's special cases / different round counts).
 __device__ __noinline__ void jl_pow_pair(double x, int n, double *pn, double *pn1) {
-  double ya = 1.0, yalo = 0.0, yb = 1.0, yblo = 0.0, xnlo = 0.0, ra = 0.0, rb = 0.0;
+  double ya = 1.0, yalo = 0.0, yb = 1.0, yblo = 0.0, xnlo = 0.0;
   int ma = n, mb = n - 1;
-  bool da = false, db = false;
-  auto fin = [&](double y, double ynlo) {
-    const double err = fma(y, xnlo, xmul(x, ynlo));
-    return (isfinite(x) && isfinite(err)) ? fma(x, y, err) : xmul(x, y);
-  };
-  while (true) {
-    if (ma == 1 && !da) { ra = fin(ya, yalo); da = true; }
-    if (mb == 1 && !db) { rb = fin(yb, yblo); db = true; }
-    if (da && db) break;
-    if (ma > 1 && (ma & 1)) {
+  while (ma > 1) {
+    if (ma & 1) {
       const double err = fma(ya, xnlo, xmul(x, yalo));
       const double hi = xmul(x, ya);
       const double lo = fma(x, ya, -hi);
       ya = hi; yalo = xadd(lo, err);
     }
-    if (mb > 1 && (mb & 1)) {
+    if (mb & 1) {
       const double err = fma(yb, xnlo, xmul(x, yblo));
       const double hi = xmul(x, yb);
       const double lo = fma(x, yb, -hi);
@@ -99,10 +92,12 @@ __device__ __noinline__ void jl_pow_pair(double x, int n, double *pn, double *pn
     const double hi2 = xmul(x, x);
     const double lo2 = fma(x, x, -hi2);
     x = hi2; xnlo = xadd(lo2, err2);
-    if (ma > 1) ma >>= 1;
-    if (mb > 1) mb >>= 1;
+    ma >>= 1; mb >>= 1;
   }
-  *pn = ra; *pn1 = rb;
+  const double ea = fma(ya, xnlo, xmul(x, yalo)), eb = fma(yb, xnlo, xmul(x, yblo));
+  const bool fx = isfinite(x);
+  *pn = (fx && isfinite(ea)) ? fma(x, ya, ea) : xmul(x, ya);
+  *pn1 = (fx && isfinite(eb)) ? fma(x, yb, eb) : xmul(x, yb);
 }
 
 // newton_solver, reference src/functions.jl:732-757 (operation for operation as the oracle)
@@ -111,7 +106,7 @@ __device__ __noinline__ int newton_solver(double S, double d, long long n, doubl
   const double Sd = xmul(S, xinv(d));
   for (int i = 1; i <= 200; ++i) {
     double xn, xn1;
-    if (n > 4 && n < 0x7fffffffll) jl_pow_pair(x, (int)n, &xn, &xn1);
+    if (n > 4 && n < 0x7fffffffll && (n & (n - 1)) != 0) jl_pow_pair(x, (int)n, &xn, &xn1);
     else { xn = jl_pow_int(x, n); xn1 = jl_pow_int(x, n - 1); }
     double omx = xsub(1.0, x);
     double Fx = xsub(xmul(xsub(1.0, xn), xinv(omx)), Sd);
