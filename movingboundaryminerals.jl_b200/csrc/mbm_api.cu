@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -38,6 +40,44 @@ int launch_rc(const char *what, cudaError_t e) {
 }
 
 // staging of one shard: device copies of host arrays, copied back on request
+// Host-buffer calls are cut into pieces that run on their own streams (one host thread each).  Left alone, all pieces
+// start their host-to-device copies at once, share the link, finish together and only then run their kernels: nothing
+// overlaps.  PieceOrder staggers them: the copies of piece q wait (on the device) for the copies of piece q-1, so piece
+// 0's kernel starts after 1/P of the input has arrived and every later copy - and every earlier piece's copy back -
+// runs beside a kernel.
+struct PieceOrder {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<int> turn;                 // per device group: the piece whose turn it is to enqueue its input copies
+  std::vector<cudaEvent_t> ev;           // per job: recorded behind the job's input copies
+  std::vector<int> group, index;         // per job: device group and position inside it
+  void begin(size_t job, cudaStream_t s) {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return turn[group[job]] == index[job]; });
+    if (index[job] > 0 && ev[job - 1]) cudaStreamWaitEvent(s, ev[job - 1], 0);
+  }
+  void end(size_t job, cudaStream_t s) {
+    if (ev[job]) cudaEventRecord(ev[job], s);
+    { std::lock_guard<std::mutex> lk(mu); turn[group[job]] = index[job] + 1; }
+    cv.notify_all();
+  }
+  // after the shard returned: pass the turn on if the shard never took it (error before its copies, or a shard kind
+  // that does not stagger), so that later pieces cannot wait for ever
+  void finish(size_t job) {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return turn[group[job]] >= index[job]; });
+    if (turn[group[job]] == index[job]) { turn[group[job]] = index[job] + 1; lk.unlock(); cv.notify_all(); }
+  }
+};
+thread_local PieceOrder *tl_order = nullptr;
+thread_local size_t tl_job = 0;
+struct PieceTurn {                       // scope of a shard's input copies
+  cudaStream_t s; bool open;
+  explicit PieceTurn(cudaStream_t st) : s(st), open(tl_order != nullptr) { if (open) tl_order->begin(tl_job, s); }
+  void done() { if (open) { tl_order->end(tl_job, s); open = false; } }
+  ~PieceTurn() { done(); }
+};
+
 struct Stage {
   struct Item { void *h; void *d; size_t bytes; bool out; };
   std::vector<Item> items;
@@ -427,6 +467,7 @@ int couple_shard(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io 
   if (own_stream) CK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
   else st.stream = g_user_stream;
   const size_t n = (size_t)(m1 - m0), capL = c->cap_left, capR = c->cap_right, H = c->hist_len;
+  PieceTurn turn(st.stream);
   mbm::KArgs A;
   memset(&A, 0, sizeof(A));
   A.M = (int)n; A.ndim = c->ndim; A.hist_len = c->hist_len; A.capL = c->cap_left; A.capR = c->cap_right;
@@ -487,6 +528,7 @@ int couple_shard(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io 
   A.node_steps = io->node_steps ? (long long *)st.inout(io->node_steps + m0, n) : nullptr;
   if ((c->flags & MBM_FLAG_RECORD) && io->rec && c->rec_cap > 0)
     A.rec = st.inout(io->rec + 4 * (size_t)c->rec_cap * (size_t)m0, 4 * (size_t)c->rec_cap * n);
+  turn.done();
   int rc = st.rc;
   if (!rc) rc = launch_shard(A, 0, (int)n, device, c->flags, st.stream, &st, ksec);
   const bool async = g_have_user_stream && st.device_ptrs;
@@ -556,7 +598,7 @@ int run_sharded(const mbm_common *c, F shard_fn) {
   const int per = (M + G - 1) / G;
   int pieces = 1;
   const bool host_buffers = !(c->flags & MBM_FLAG_DEVICE_POINTERS) && !g_have_user_stream;
-  if (host_buffers && per >= 2048) pieces = 4;
+  if (host_buffers && per >= 2048) pieces = (per >= 4096) ? 8 : 4;
   if (const char *e = getenv("MBM_PIECES")) { const int p = atoi(e); if (p >= 1 && p <= 16) pieces = p; }
   if (!host_buffers) pieces = 1;
   struct Job { int m0, m1, dev, g; };
@@ -581,13 +623,27 @@ int run_sharded(const mbm_common *c, F shard_fn) {
     rcs[0] = shard_fn(jobs[0].m0, jobs[0].m1, jobs[0].dev, &ks[0]);
     nl[0] = g_last_kernel_launches;
   } else {
+    PieceOrder order;
+    const bool staggered = pieces > 1 && !getenv("MBM_NO_STAGGER");
+    if (staggered) {
+      order.turn.assign(G, 0); order.ev.assign(J, nullptr); order.group.resize(J); order.index.resize(J);
+      for (size_t j = 0; j < J; ++j) {
+        order.group[j] = jobs[j].g;
+        order.index[j] = (j > 0 && jobs[j - 1].g == jobs[j].g) ? order.index[j - 1] + 1 : 0;
+        if (cudaSetDevice(jobs[j].dev) == cudaSuccess) cudaEventCreateWithFlags(&order.ev[j], cudaEventDisableTiming);
+      }
+    }
     std::vector<std::thread> th;
     for (size_t j = 0; j < J; ++j)
       th.emplace_back([&, j]() {
+        if (staggered) { tl_order = &order; tl_job = j; }
         rcs[j] = shard_fn(jobs[j].m0, jobs[j].m1, jobs[j].dev, &ks[j]);
         nl[j] = g_last_kernel_launches;
+        tl_order = nullptr;
+        if (staggered) order.finish(j);
       });
     for (auto &t : th) t.join();
+    for (cudaEvent_t e : order.ev) if (e) cudaEventDestroy(e);
   }
   cudaSetDevice(prev_dev);
   double k0 = 0.0;
