@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MBM_ABI_VERSION 2
+#define MBM_ABI_VERSION 3
 
 /* ---- interface condition (which `set_inner_bc_*` the step uses) -------------------- */
 enum {
@@ -46,6 +46,18 @@ enum {
   MBM_DT_ADVECTIVE = 1, /* dt = minimum([dx1,dx2])/V_ip*CFL, examples/C1.jl:93, B4.jl:93      */
   MBM_DT_STEFAN    = 2, /* Chemical_Stefan_problem_XT.jl:79,147-149 (dt carried in io.dt)     */
   MBM_DT_SIMPLE    = 3  /* calculate_dt, src/functions.jl:164-168                             */
+};
+
+/* ---- in-loop material laws (Stefan driver), mbm_couple_params.law ------------------------ */
+enum {
+  MBM_LAW_NONE = 0,            /* D_l, D_r stay params.Di (Chemical_Stefan_problem_XT.jl:63-64)        */
+  /* examples/D1.jl:126-132: every step, after the interface compositions are set,
+   *   log10D = law_par[0] - law_par[1]/(2.303*R*T) + 3*(mean(C_left) - 0.14)        (Dohmen & Chakraborty 2007)
+   *   D_l    = 10^log10D*law_par[2] + 10^(log10D - log10(6))*law_par[3] + 10^(log10D - log10(6))*law_par[4]
+   *   D_r    = exp(-7.92 - 26222/T)                                                  (Zhang & Cherniak 2010)
+   * law_par = { log10(D0), Ea + (P-1e5)*deltaV, cos(alpha)^2, cos(beta)^2, cos(gamma)^2, 0, 0, 0 };
+   * mean(C_left) = canonical sum / node count.                                      */
+  MBM_LAW_OLIVINE_MELT_D1 = 1
 };
 
 /* ---- flags ---------------------------------------------------------------------------- */
@@ -132,11 +144,12 @@ typedef struct mbm_couple_params {
   const double *C_leftB;    /* [M] initial equilibrium compositions used by calculate_density */
   const double *C_rightB;   /* [M]                                                            */
   int32_t nd;               /* density table is nd x nd; 0 = no table, rho stays params.rho   */
-  int32_t reserved;
+  int32_t law;              /* MBM_LAW_*: in-loop material law of the Stefan driver (0 = none)   */
   const double *dens_X;     /* [nd]     Xwm[:,1]                                              */
   const double *dens_T;     /* [nd]     Twm[1,:]                                              */
   const double *dens_left;  /* [nd,nd]  column-major                                          */
   const double *dens_right; /* [nd,nd]                                                        */
+  const double *law_par;    /* [8,M] parameters of `law` (NULL for MBM_LAW_NONE), see MBM_LAW_*  */
 } mbm_couple_params;
 
 /* in/out state of a couple ensemble; calling again with the returned state resumes the run

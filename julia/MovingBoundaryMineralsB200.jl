@@ -14,7 +14,7 @@ module MovingBoundaryMineralsB200
 using MovingBoundaryMinerals: scaling, rescale            # host-side pre/post steps stay the reference's own
 
 const LIB = get(ENV, "MBM_B200_LIB", joinpath(@__DIR__, "..", "movingboundaryminerals.jl_b200", "csrc", "libmbm_b200.so"))
-const ABI_VERSION = Int32(2)
+const ABI_VERSION = Int32(3)
 const BC_FLUX, BC_MB, BC_STEFAN, BC_HOLD = Int32(1), Int32(2), Int32(3), Int32(4)
 const DT_FIND_DT, DT_ADVECTIVE, DT_STEFAN, DT_SIMPLE = Int32(0), Int32(1), Int32(2), Int32(3)
 const FLAG_RECORD, FLAG_MASS_FINAL = UInt32(0x0002), UInt32(0x0080)
@@ -31,8 +31,9 @@ struct CoupleParams                # mbm_couple_params
     t_ar::Ptr{Float64}; T_ar::Ptr{Float64}; KD_ar::Ptr{Float64}
     t_stride::Int64; T_stride::Int64; KD_stride::Int64; R::Float64
     coeff_up::Ptr{Float64}; coeff_do::Ptr{Float64}; coeff_stride::Int64
-    C_leftB::Ptr{Float64}; C_rightB::Ptr{Float64}; nd::Int32; reserved::Int32
+    C_leftB::Ptr{Float64}; C_rightB::Ptr{Float64}; nd::Int32; law::Int32
     dens_X::Ptr{Float64}; dens_T::Ptr{Float64}; dens_left::Ptr{Float64}; dens_right::Ptr{Float64}
+    law_par::Ptr{Float64}         # [8,M] for law = 1 (examples/D1.jl:126-132), else C_NULL
 end
 
 struct CoupleIO                    # mbm_couple_io
@@ -94,7 +95,7 @@ function couple_ensemble(pars::AbstractVector; kind::Symbol = :mb, dt_mode::Int3
         c = Ref(Common(ABI_VERSION, M, n, H, capL, capR, inner, dt_mode, FLAG_MASS_FINAL, Int32(n_devices), max_steps, C_NULL, 0))
         p = Ref(CoupleParams(pointer(Di), pointer(D0), pointer(Ea), pointer(rho), pointer(V), pointer(ttot), pointer(CFL),
                              pointer(MRefin), pointer(BCout), pointer(resmin), pointer(t_ar), pointer(T_ar), pointer(KD_ar),
-                             H, H, H, pars[1].R, C_NULL, C_NULL, 0, C_NULL, C_NULL, 0, 0, C_NULL, C_NULL, C_NULL, C_NULL))
+                             H, H, H, pars[1].R, C_NULL, C_NULL, 0, C_NULL, C_NULL, 0, 0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL))
         io = Ref(CoupleIO(pointer(x_left), pointer(C_left), pointer(x_right), pointer(C_right), pointer(res), pointer(Ri),
                           pointer(t), pointer(dt), pointer(it), pointer(dx1), pointer(dx2), pointer(Mass0), pointer(Mass),
                           pointer(nR), pointer(last), pointer(status), pointer(warn), pointer(hash), pointer(node_steps), C_NULL))

@@ -11,7 +11,8 @@ from pathlib import Path
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+LAW_NONE, LAW_OLIVINE_MELT_D1 = 0, 1      # mbm_couple_params.law (examples/D1.jl:126-132)
 
 # interface conditions / dt rules / flags (include/mbm_b200.h)
 BC_NONE, BC_FLUX, BC_MB, BC_STEFAN, BC_DIRICHLET_HOLD = 0, 1, 2, 3, 4
@@ -55,8 +56,8 @@ class CoupleParams(C.Structure):
         ("t_stride", C.c_int64), ("T_stride", C.c_int64), ("KD_stride", C.c_int64),
         ("R", C.c_double),
         ("coeff_up", _dp), ("coeff_do", _dp), ("coeff_stride", C.c_int64),
-        ("C_leftB", _dp), ("C_rightB", _dp), ("nd", C.c_int32), ("reserved", C.c_int32),
-        ("dens_X", _dp), ("dens_T", _dp), ("dens_left", _dp), ("dens_right", _dp),
+        ("C_leftB", _dp), ("C_rightB", _dp), ("nd", C.c_int32), ("law", C.c_int32),
+        ("dens_X", _dp), ("dens_T", _dp), ("dens_left", _dp), ("dens_right", _dp), ("law_par", _dp),
     ]
 
 

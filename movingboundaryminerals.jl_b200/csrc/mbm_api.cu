@@ -495,6 +495,8 @@ int couple_shard(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io 
     A.C_leftB = st.in(p->C_leftB + m0, n);
     A.C_rightB = st.in(p->C_rightB + m0, n);
     A.nd = p->nd;
+    A.law = p->law_par ? p->law : MBM_LAW_NONE;
+    if (A.law) A.law_par = st.in(p->law_par + 8 * (size_t)m0, 8 * n);
     if (p->nd > 0) {
       A.dens_X = st.in(p->dens_X, (size_t)p->nd);
       A.dens_T = st.in(p->dens_T, (size_t)p->nd);

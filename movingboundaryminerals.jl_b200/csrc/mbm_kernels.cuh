@@ -27,8 +27,8 @@ struct KArgs {
   const double *coeff_up, *coeff_do;
   long long coeff_stride;
   const double *C_leftB, *C_rightB;
-  int nd, pad2_;
-  const double *dens_X, *dens_T, *dens_left, *dens_right;
+  int nd, law;            // law: MBM_LAW_* (examples/D1.jl in-loop diffusivities), law_par [8,M]
+  const double *dens_X, *dens_T, *dens_left, *dens_right, *law_par;
   // state
   double *x_left, *C_left, *x_right, *C_right;
   long long *res;
@@ -67,6 +67,7 @@ struct Scal {
   double a_if, b_if, Co_first, Co_last;
   double KDmin, KDmax, Tmin, Tmax, tmin, tmax;
   double cu0, cu1, cu2, cd0, cd1, cd2, CLB, CRB;
+  double lp0, lp1, lp2, lp3, lp4;    // parameters of the in-loop material law (MBM_LAW_OLIVINE_MELT_D1)
   double grid_d, grid_S, grid_total;
   double red[128];
   double recbuf[16];                 // tuned kernel: the next step's record, staged by cp.async
@@ -243,6 +244,37 @@ __device__ inline int interp2(const double *X1d, const double *Y1d, const double
   return 0;
 }
 
+// Last element of the canonical inclusive sum scan of v[0..n-1] (scan_canonical), evaluated by ONE thread with the
+// same operations in the same order: sequential inside tiles of 9, Hillis-Steele over the 32 tile totals of a group,
+// sequential over groups.  Used for mean(C_left) of the D1 material law (the Stefan profiles are a few dozen nodes).
+__device__ inline double canonical_total_serial(const double *v, int n) {
+  const int last = n - 1, gl = last / CSO_GROUP_ELEMS;
+  double Og = 0.0, res = 0.0;
+  for (int g = 0; g <= gl; ++g) {
+    double inc[32], loc_last = 0.0;
+    for (int q = 0; q < 32; ++q) {
+      const int base = (g * 32 + q) * CSO_TILE;
+      double sacc = 0.0;
+      for (int k = 0; k < CSO_TILE; ++k) {
+        const int i = base + k;
+        if (i >= n) break;
+        sacc = (k == 0) ? v[i] : xadd(sacc, v[i]);
+        if (i == last) loc_last = sacc;
+      }
+      inc[q] = sacc;
+    }
+    for (int off = 1; off < 32; off <<= 1)
+      for (int q = 31; q >= off; --q) inc[q] = xadd(inc[q - off], inc[q]);
+    if (g == gl) {
+      const int q = (last / CSO_TILE) % 32;
+      const double pq = (q == 0) ? loc_last : xadd(inc[q - 1], loc_last);
+      res = (g == 0) ? pq : xadd(Og, pq);
+    }
+    Og = (g == 0) ? inc[31] : xadd(Og, inc[31]);
+  }
+  return res;
+}
+
 // ---- scalar phase of one step (thread 0): dt, time, parameters, interface advection, new node counts ---
 __device__ inline void step_scalars(Scal &S, const KArgs &A, const MemberPtrs &P, int mem, double *X, double *C) {
   const int bc = A.inner_bc;
@@ -286,6 +318,14 @@ __device__ inline void step_scalars(Scal &S, const KArgs &A, const MemberPtrs &P
       if (rc) { S.status = rc; return; }
       S.rho1 = rL * (1.0 / rL);
       S.rho2 = rR * (1.0 / rL);
+    }
+    if (A.law == 1) {                                                      // MBM_LAW_OLIVINE_MELT_D1, examples/D1.jl:126-132
+      const double meanC = xdiv(canonical_total_serial(C, n1), (double)n1);
+      const double l001 = xadd(xsub(S.lp0, xdiv(S.lp1, xmul(xmul(2.303, S.R), Tt))), xmul(3.0, xsub(meanC, 0.14)));
+      const double loth = xsub(l001, 0.7781512503836436);           // log10(6.0)
+      const double D001 = pow(10.0, l001), Doth = pow(10.0, loth);
+      S.D_l = xadd(xadd(xmul(D001, S.lp2), xmul(Doth, S.lp3)), xmul(Doth, S.lp4));
+      S.D_r = exp(xsub(-7.92, xdiv(26222.0, Tt)));
     }
     const double JL = -S.D_l * S.rho1 * (C[n1 - 1] - C[n1 - 2]) * (1.0 / S.dx1);   // CSP :111
     const double JR = -S.D_r * S.rho2 * (C[rb + 1] - C[rb]) * (1.0 / S.dx2);       // :112
@@ -730,6 +770,10 @@ __global__ void __launch_bounds__(T) mbm_step_kernel(const KArgs A, const int me
         const double *cu = A.coeff_up + (size_t)mem * A.coeff_stride, *cd = A.coeff_do + (size_t)mem * A.coeff_stride;
         S.cu0 = cu[0]; S.cu1 = cu[1]; S.cu2 = cu[2]; S.cd0 = cd[0]; S.cd1 = cd[1]; S.cd2 = cd[2];
         S.CLB = A.C_leftB[mem]; S.CRB = A.C_rightB[mem];
+        if (A.law == 1 && A.law_par) {
+          const double *lp = A.law_par + 8 * (size_t)mem;
+          S.lp0 = lp[0]; S.lp1 = lp[1]; S.lp2 = lp[2]; S.lp3 = lp[3]; S.lp4 = lp[4];
+        }
       }
     }
     if (A.ndim < 1 || A.ndim > 3) { if (!S.status) S.status = 7; }

@@ -384,8 +384,31 @@ def pars_CSP():
                 coeff=COEFF_REACTION_LINES, CFL=0.8, res=[15, 25], MRefin=5.0, BCout=[0, 0], hist_len=10000)
 
 
+def pars_D1():
+    """examples/D1.jl:8-35: olivine / melt Stefan problem with in-loop diffusivities (olivine after Dohmen &
+    Chakraborty 2007 as a function of T and the mean olivine composition, melt after Zhang & Cherniak 2010);
+    the density table is replaced by ones exactly as D1.jl:54-55 does.  Angles are passed to cos() as written
+    in the reference (90.0 is taken in radians there)."""
+    return dict(D0=5.38 * 1e-9, Ea=226000, alpha=0.0, beta=90.0, gamma=90.0, deltaV=7 * 0.1**6, P=10**6, R=8.314472,
+                Ri=0.0001, Tstart=1400.0 + 273.0, Tstop=1350.0 + 273.0, t_tot=60 * 60 * 24 * 30, n=1, CompInt=0.50,
+                coeff=COEFF_REACTION_LINES, CFL=50.0, res=[50, 50], MRefin=5.0, BCout=[0, 0], hist_len=10000,
+                law=abi.LAW_OLIVINE_MELT_D1)
+
+
+def d1_diffusivities(p, T, meanC):
+    """examples/D1.jl:68-74 / :126-132 (host side: initial values, used for the first dt only)"""
+    import math
+    l001 = math.log10(p["D0"]) - (p["Ea"] + (p["P"] - 10**5) * p["deltaV"]) / (2.303 * p["R"] * T) + 3 * (meanC - 0.14)
+    loth = l001 - math.log10(6.0)
+    D001, Doth = 10**l001, 10**loth
+    D_l = D001 * math.cos(p["alpha"]) ** 2 + Doth * math.cos(p["beta"]) ** 2 + Doth * math.cos(p["gamma"]) ** 2
+    D_r = math.exp(-7.92 - 26222 / T)
+    return D_l, D_r
+
+
 def build_stefan_ensemble(pars_list, lib=None, cap_left=None, cap_right=None):
-    """Pre-loop part of CSP() (Chemical_Stefan_problem_XT.jl:27-98) for a list of members."""
+    """Pre-loop part of CSP() (Chemical_Stefan_problem_XT.jl:27-98) and of D1() (examples/D1.jl:36-97) for a list
+    of members; members with a `law` entry carry the in-loop material law of D1."""
     lib = _lib(lib)
     M = len(pars_list)
     p0 = pars_list[0]
@@ -393,11 +416,16 @@ def build_stefan_ensemble(pars_list, lib=None, cap_left=None, cap_right=None):
     res_max = np.max([p["res"] for p in pars_list], axis=0)
     cap_left = cap_left or int(4 * res_max[0] + 8)
     cap_right = cap_right or int(4 * res_max[1] + 8)
+    law = int(p0.get("law", abi.LAW_NONE))
+    assert all(int(p.get("law", abi.LAW_NONE)) == law for p in pars_list), "all members must share the material law"
     ens = CoupleEnsemble(M, int(p0["n"]), abi.BC_STEFAN, abi.DT_STEFAN, cap_left, cap_right, hist_len, R=8.314472,
                          arrays=dict(t_ar=np.zeros((M, hist_len)), T_ar=np.zeros((M, hist_len)),
                                      KD_ar=np.zeros((1, hist_len)), coeff_up=np.zeros((M, 3)), coeff_do=np.zeros((M, 3)),
-                                     C_leftB=np.zeros(M), C_rightB=np.zeros(M)))
+                                     C_leftB=np.zeros(M), C_rightB=np.zeros(M),
+                                     law_par=np.zeros((M, 8)) if law else None))
     a = ens.arrays
+    if law:
+        a["law"] = law
     for m, p in enumerate(pars_list):
         coeff = np.asarray(p["coeff"], float)
         coeff_up, coeff_do = coeff[:, 0].copy(), coeff[:, 1].copy()          # :17-19, coeff_trans_line
@@ -412,6 +440,11 @@ def build_stefan_ensemble(pars_list, lib=None, cap_left=None, cap_right=None):
         a["coeff_up"][m], a["coeff_do"][m], a["C_leftB"][m], a["C_rightB"][m] = coeff_up, coeff_do, CLB, CRB
         a["Ri"][m] = [Ri0, L]
         a["res"][m] = p["res"]; a["resmin"][m] = p["res"]
+        if law:                                                                # D1.jl:68-74: D(T, X) at Tstart
+            import math
+            p["Di"] = list(d1_diffusivities(p, T, CLB))
+            a["law_par"][m, :5] = [math.log10(p["D0"]), p["Ea"] + (p["P"] - 10**5) * p["deltaV"],
+                                   math.cos(p["alpha"]) ** 2, math.cos(p["beta"]) ** 2, math.cos(p["gamma"]) ** 2]
         a["Di"][m] = p["Di"]; a["rho"][m] = [1.0, 1.0]
         a["t_tot"][m], a["CFL"][m], a["MRefin"][m], a["BCout"][m] = p["t_tot"], p["CFL"], p["MRefin"], p["BCout"]
         a["T_ar"][m] = linrange(p["Tstart"], p["Tstop"], hist_len)             # Tpath :51
@@ -428,11 +461,22 @@ def build_stefan_ensemble(pars_list, lib=None, cap_left=None, cap_right=None):
     return ens
 
 
+def D1(lib=None, **over):
+    """examples/D1.jl:4-233 (the entries of its 25-tuple that do not need plots): the Stefan driver with the
+    olivine / melt diffusivities recomputed every step -> dict(x_left, x_right, x0, C_left, C_right, C0, maxC, T,
+    Mass0, Mass, KD_sim, T_sim, Ri, it)"""
+    p = pars_D1(); p.update(over)
+    out = CSP(lib, _pars=p)
+    out["maxC"] = float(max(out["C_left"].max(), out["C_right"].max()))
+    return out
+
+
 def CSP(lib=None, **over):
     """main_codes/Chemical_Stefan_problem_XT.jl:4-208 (subset of the 20-tuple that does not need plots):
     -> dict(x_left, x_right, x0, C_left, C_right, C0, T, Mass0, Mass, KD_sim, T_sim, Ri, it)"""
     lib = _lib(lib)
-    p = pars_CSP(); p.update(over)
+    p = over.pop("_pars", None) or pars_CSP()
+    p.update(over)
     ens = build_stefan_ensemble([p], lib)
     x0 = np.concatenate([ens.member(0)[0], ens.member(0)[2]]).copy()
     C0 = np.concatenate([ens.member(0)[1], ens.member(0)[3]]).copy()

@@ -105,6 +105,7 @@ class CoupleEnsemble:
         a.setdefault("coeff_up", None); a.setdefault("coeff_do", None)
         a.setdefault("C_leftB", None); a.setdefault("C_rightB", None)
         a.setdefault("dens", None)  # (X[nd], T[nd], left[nd,nd], right[nd,nd]) or None
+        a.setdefault("law_par", None)  # [M,8] parameters of the in-loop material law (examples/D1.jl), or None
         a.setdefault("rec", None)
 
     def __getattr__(self, name):
@@ -145,6 +146,8 @@ class CoupleEnsemble:
             X, T, L, Rr = a["dens"]
             p.nd = len(X)
             p.dens_X, p.dens_T, p.dens_left, p.dens_right = abi.dptr(X), abi.dptr(T), abi.dptr(L), abi.dptr(Rr)
+        if a.get("law_par") is not None:
+            p.law = int(a.get("law", abi.LAW_OLIVINE_MELT_D1)); p.law_par = abi.dptr(a["law_par"])
         io = abi.CoupleIO()
         for n in ("x_left", "C_left", "x_right", "C_right", "Ri", "t", "dt", "dx1", "dx2", "Mass0", "Mass",
                   "newton_R", "last"):

@@ -190,6 +190,8 @@ typedef struct {
   double C_leftB, C_rightB;
   int nd;
   const double *dens_X, *dens_T, *dens_left, *dens_right;
+  int law;
+  double law_par[8];
   /* state (arrays have capacity cap+1 so that the transient inserted node always fits) */
   double *xl, *cl, *xr, *cr;
   int64_t n1, n2;
@@ -639,6 +641,18 @@ static int couple_step(member_t *m, scratch_t *sc) {
       rho[1] = rR * jl_inv(rL);
     }
     m->rho[0] = rho[0]; m->rho[1] = rho[1];
+    if (m->law == MBM_LAW_OLIVINE_MELT_D1) {                                              /* examples/D1.jl:126-132 */
+      /* mean(C_left) after C_left[end] was set: canonical sum / length (Julia's pairwise `sum` is not reproducible
+       * between builds; the canonical order is shared with the CUDA kernels)                                       */
+      double *cs = scratch_get(sc, (size_t)m->n1 + 8);
+      scan_canonical(m->cl, m->n1, cs, 0);
+      double meanC = cs[m->n1 - 1] / (double)m->n1;
+      double l001 = (m->law_par[0] - m->law_par[1] / ((2.303 * m->R) * T)) + 3.0 * (meanC - 0.14);       /* :126 */
+      double loth = l001 - 0.7781512503836436 /* log10(6.0) */;                                                                 /* :127 */
+      double D001 = pow(10.0, l001), Doth = pow(10.0, loth);                                             /* :128-130 */
+      m->D_l = (D001 * m->law_par[2] + Doth * m->law_par[3]) + Doth * m->law_par[4];                     /* :131 */
+      m->D_r = exp(-7.92 - 26222.0 / T);                                                                 /* :132 */
+    }
     double JL = -m->D_l * rho[0] * (m->cl[m->n1 - 1] - m->cl[m->n1 - 2]) * jl_inv(m->dx1); /* :111 */
     double JR = -m->D_r * rho[1] * (m->cr[1] - m->cr[0]) * jl_inv(m->dx2);                 /* :112 */
     V_ip = (JR - JL) * jl_inv(dC);                                                         /* :113 */
@@ -902,6 +916,8 @@ int mbm_couple_batch(const mbm_common *c, const mbm_couple_params *p, mbm_couple
         m.C_leftB = p->C_leftB[k]; m.C_rightB = p->C_rightB[k];
         m.nd = p->nd; m.dens_X = p->dens_X; m.dens_T = p->dens_T;
         m.dens_left = p->dens_left; m.dens_right = p->dens_right;
+        m.law = p->law_par ? p->law : MBM_LAW_NONE;
+        if (m.law) for (int j = 0; j < 8; ++j) m.law_par[j] = p->law_par[8 * k + j];
       }
       m.xl = xl; m.cl = cl; m.xr = xr; m.cr = cr;
       m.n1 = io->res[2 * k]; m.n2 = io->res[2 * k + 1];

@@ -297,3 +297,26 @@ def test_streaming_interleaved_kernel(oracle, cuda_lib, kind):
     assert eo.run(oracle, max_steps=120) == 0
     assert eg.run(cuda_lib, max_steps=120, flags=abi.FLAG_FORCE_STREAMING) == 0
     compare(eo, eg)
+
+
+def test_D1_material_law(oracle, cuda_lib):
+    """examples/D1.jl: Stefan driver with the olivine / melt diffusivities recomputed every step from T and the mean
+    olivine composition (MBM_LAW_OLIVINE_MELT_D1).  CUDA `pow`/`exp` and glibc's differ by an ulp in D, which feeds
+    dt, and V comes from the solution: values are held to 2e-9 as for the Arrhenius / Stefan fixtures; node counts and
+    step counts must agree exactly (the regrid checksum is not compared: with meshes that differ in the last bits the
+    equal / clamp branch of the last node is not defined, as in test_stefan_main)."""
+    pars = []
+    for Tstop, comp in ((1350.0 + 273.0, 0.50), (1330.0 + 273.0, 0.45), (1375.0 + 273.0, 0.55)):
+        p = d.pars_D1(); p.update(Tstop=Tstop, CompInt=comp); pars.append(p)
+    eo = d.build_stefan_ensemble(pars, oracle)
+    eg = d.build_stefan_ensemble(pars, cuda_lib)
+    assert eo.run(oracle, max_steps=3000, flags=abi.FLAG_MASS_FINAL) == 0
+    assert eg.run(cuda_lib, max_steps=3000, flags=abi.FLAG_MASS_FINAL) == 0
+    assert np.array_equal(eo.status, eg.status) and np.all(eo.status == 0)
+    for k in ("res", "it", "node_steps"):
+        assert np.array_equal(eo.arrays[k], eg.arrays[k]), k
+    for m in range(eo.M):
+        for a, b in zip(eo.member(m), eg.member(m)):
+            assert _relerr(a, b) < 2e-9
+    assert _relerr(eo.Ri, eg.Ri) < 1e-10
+    assert _relerr(eo.last[:, :2], eg.last[:, :2]) < 1e-12       # D_l, D_r of the last step

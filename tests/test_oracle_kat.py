@@ -137,3 +137,24 @@ def test_newton_warm_vs_cold(oracle):
     assert np.max(np.abs(a["x_right"] - b["x_right"])) <= 1e-12 * np.max(np.abs(a["x_right"]))
     assert np.max(np.abs(a["C_right"] - b["C_right"])) <= 5e-9 * np.max(np.abs(a["C_right"]))
     assert np.max(np.abs(a["C_left"] - b["C_left"])) <= 5e-9 * np.max(np.abs(a["C_left"]))
+
+
+def test_D1_material_law_prefix(oracle):
+    """examples/D1.jl (no test in the reference; the whole run is 6.6 million steps): first 2000 steps through the
+    oracle.  The diffusivities reported after the last step must be the D1 laws (D1.jl:126-132) evaluated at the
+    current temperature and mean olivine composition; olivine grows while the melt cools; closed-system mass drift
+    stays at the level of the Stefan main code."""
+    import math
+    p = d.pars_D1()
+    ens = d.build_stefan_ensemble([p], oracle)
+    assert ens.run(oracle, max_steps=2000, flags=abi.FLAG_MASS_FINAL) == 0
+    assert ens.status[0] == 0 and ens.it[0] == 2000
+    xl, cl, xr, cr = ens.member(0)
+    D_l, D_r, KD, T = ens.last[0, :4]
+    assert 1623.0 < T < 1673.0
+    # the law used mean(C_left) before the step's solve; after 2000 tiny steps it has moved by < 1e-6 relative
+    Dl_ref, Dr_ref = d.d1_diffusivities(p, T, float(np.mean(cl)))
+    assert abs(D_r - Dr_ref) <= 1e-12 * Dr_ref
+    assert abs(D_l - Dl_ref) <= 1e-4 * Dl_ref
+    assert ens.Ri[0, 0] > p["Ri"]                                  # olivine grows on cooling
+    assert abs((ens.Mass[0] - ens.Mass0[0]) / ens.Mass0[0]) < 2e-3
