@@ -10,7 +10,8 @@ is larger than L2 (126 MB).
   value    node-steps/s, all ranks, state resident in HBM when the timed region starts
            (MBM_FLAG_DEVICE_POINTERS; CUDA events on the launching stream; max over ranks)
   e2e      the same metric through the reference-facing C-ABI call with HOST (pinned) buffers:
-           H2D of the state + kernel + D2H of the result inside the timed region
+           H2D of the state + kernel + D2H of the result inside the timed region (the library cuts the
+           call into 8 pieces whose input copies are staggered, so copies run beside kernels)
   roofline FP64 pipe: algorithmic flops per node-step (100 for MB, n = 2) x node-steps/s
            over the DFMA peak measured live; the HBM figure (32 B/node-step) is reported beside it
   cpu_baseline  the CPU oracle (structured O(N) solve, OpenMP over members, all host cores) on a bounded
@@ -282,7 +283,7 @@ def main():
         e2e = {"value": float(tn.item()) / float(te.item()), "unit": "node-steps/s", "h2d_bytes_per_step": int(h2d) * world,
                "d2h_bytes_per_step": int(d2h) * world, "bytes_are": "whole job (all ranks)", "steps": ke,
                "ms_per_step": 1e3 * float(te.item()) / ke,
-               "api": "mbm_couple_batch with host (pinned) buffers: H2D + kernels + D2H inside the call, pipelined over 4 streams"}
+               "api": "mbm_couple_batch with host (pinned) buffers: H2D + kernels + D2H inside the call, 8 pieces on their own streams, input copies staggered piece by piece"}
         del pinned
 
     if rank != 0:
