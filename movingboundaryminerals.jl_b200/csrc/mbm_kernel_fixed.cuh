@@ -8,7 +8,8 @@
 //   R_l = mli*C_{l-1} + mdi*C_l + mui*C_{l+1} - fs*R_{l-1}      (right-hand side + forward substitution, 4 FMA/row)
 //   backward accumulation of the chunk's first row, reduced solve (warp 0), 2x2 interface condition, back-substitution.
 // A step whose (dt, D_l, D_r) differ from the factorised ones first re-runs the coefficient sweep (same arithmetic as
-// the tuned moving-interface kernel).  Loop body: reference main_codes/Diff_couple_1D_general_Flux.jl:87-130 with
+// the tuned moving-interface kernel).  The right phase is stored by REVERSED node index (right node j at N-1-j), so
+// both blocks sweep with increasing storage index and every access of the row loops is base + immediate.  Loop body: reference main_codes/Diff_couple_1D_general_Flux.jl:87-130 with
 // Fl_regrid == 0 (functions.jl:58-61), examples/Diff_couple_MB.jl:87-109, Diff_couple_no_interaction.jl:96-124.
 #pragma once
 #include "mbm_kernel_v2.cuh"
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, co
     const double *gxl = A.x_left + (size_t)mem * A.capL, *gcl = A.C_left + (size_t)mem * A.capL;
     const double *gxr = A.x_right + (size_t)mem * A.capR, *gcr = A.C_right + (size_t)mem * A.capR;
     for (int i = tid; i < n1; i += T) { X[i] = gxl[i]; C[i] = gcl[i]; }
-    for (int i = tid; i < n2; i += T) { X[rb + i] = gxr[i]; C[rb + i] = gcr[i]; }
+    for (int i = tid; i < n2; i += T) { X[N - 1 - i] = gxr[i]; C[N - 1 - i] = gcr[i]; }     // reversed storage
     double v[4] = {1e300, -1e300, 1e300, -1e300}, tm[2] = {1e300, -1e300};
     for (int i = tid; i < A.hist_len; i += T) {
       const double tt = P.t_ar[i], TT = P.T_ar[i], kd = P.KD_ar[i];
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, co
       }
       S.KDmin = a0; S.KDmax = a1; S.Tmin = a2; S.Tmax = a3; S.tmin = a4; S.tmax = a5;
       S.dx1 = xsub(X[n1 - 1], X[n1 - 2]);                                   // create_grid!, functions.jl:366-367
-      S.dx2 = xsub(X[rb + 1], X[rb]);
+      S.dx2 = xsub(X[N - 2], X[N - 1]);                                     // x_right[2] - x_right[1]
       const int rc = update_t_dependent(S, A, P, false);                   // pre-loop call (e.g. B1.jl:72)
       if (rc) S.status = rc;
     }
@@ -114,8 +115,8 @@ __global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, co
   const int nb = blk ? nbR : nbL;
   const int f = jc * m;
   const int len = active ? (min(f + m, nb) - f) : 0;
-  const int sdir = blk ? -1 : 1;
-  const int s0 = blk ? (N - 1 - f) : f;
+  const bool xdec = (blk != 0);              // x decreases along the sweep of the right block (it starts at the outer end)
+  const int s0 = blk ? (rb + f) : f;         // storage index of local row f: both blocks sweep upwards
   const bool lastChunk = active && (jc == (blk ? KR : KL) - 1);
   const bool dir0 = blk ? (S.bc1 == 1) : (S.bc0 == 1);
   // per-chunk constants of the factorisation (registers)
@@ -162,23 +163,23 @@ __global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, co
         double pAc = 0.0, pAnext = 0.0, pkk = 0.0;
         const bool haveP0 = f > 0;
         if (haveP0) {
-          x_prev = X[s0 - sdir];
+          x_prev = X[s0 - 1];
           double A11, A12, A22, kk;
-          if (sdir > 0) elem_mats_fast<NDIM>(x_prev, x_self, Dph, idt, A11, A12, A22, kk);
+          if (!xdec) elem_mats_fast<NDIM>(x_prev, x_self, Dph, idt, A11, A12, A22, kk);
           else elem_mats_fast<NDIM>(x_self, x_prev, Dph, idt, A11, A12, A22, kk);
-          pAnext = (sdir > 0) ? A22 : A11; pAc = A12; pkk = kk;
+          pAnext = (!xdec) ? A22 : A11; pAc = A12; pkk = kk;
         }
         double Ap = 0.0, Gp = 0.0, Qb = 0.0, Qa = 0.0, Qc = 0.0;
         double Vs = 0.0, Vm = 0.0;
         if (mb) { Vs = powd<NDIM>(x_self); Vm = haveP0 ? powd<NDIM>(x_prev) : Vs; }
         int s = s0;
 #pragma unroll 1
-        for (int k = 0; k < len; ++k, s += sdir) {
-          const double x_next = X[s + sdir];
+        for (int k = 0; k < len; ++k, ++s) {
+          const double x_next = X[s + 1];
           double A11, A12, A22, kk;
-          if (sdir > 0) elem_mats_fast<NDIM>(x_self, x_next, Dph, idt, A11, A12, A22, kk);
+          if (!xdec) elem_mats_fast<NDIM>(x_self, x_next, Dph, idt, A11, A12, A22, kk);
           else elem_mats_fast<NDIM>(x_next, x_self, Dph, idt, A11, A12, A22, kk);
-          const double nAself = (sdir > 0) ? A11 : A22, nAnext = (sdir > 0) ? A22 : A11;
+          const double nAself = (!xdec) ? A11 : A22, nAnext = (!xdec) ? A22 : A11;
           double diag = (nAself - kk) + (pAnext - pkk);
           double ml = pAc, md = nAself + pAnext, mu = A12;            // mass-matrix row / dt: rhs = ml*C- + md*C + mu*C+
           double sup = A12 + kk, sub = pAc + pkk;
@@ -201,10 +202,10 @@ __global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, co
         // backward accumulation of the matrix part (bA, bG): first row of the chunk in terms of the two separators
         cbA = 0.0; cbG = -1.0;
         if (len > 1) {
-          int sb = s0 + sdir * (len - 2);
+          int sb = s0 + (len - 2);
           cbA = FA[sb]; cbG = FG[sb];
 #pragma unroll 1
-          for (int k = len - 3; k >= 0; --k) { sb -= sdir; const double Gk = FG[sb]; cbA = FA[sb] - Gk * cbA; cbG = -Gk * cbG; }
+          for (int k = len - 3; k >= 0; --k) { --sb; const double Gk = FG[sb]; cbA = FA[sb] - Gk * cbA; cbG = -Gk * cbG; }
         }
         exA[tid] = cbA; exG[tid] = cbG;
       }
@@ -223,15 +224,26 @@ __global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, co
       if (tid < 32) reduced_solve<T, 2>(redS, redD, redU, red0, red1);
       __syncthreads();
       red1c[tid] = red1[tid];
+      if (bc == BC_FLUX) {
+        // the flux row's coefficients only change with the factorisation: al*U + (be + al*U1)*a + (ga + de*W1)*b + de*W = 0
+        __syncthreads();
+        if (tid == 0) {
+          const int p_ = n1 - 1, q_ = N - 1;
+          const double idxl = frcp(X[p_] - X[p_ - 1]), idxr = frcp(X[q_ - 1] - X[q_]);
+          const double al = -S.rho1 * S.D_l * idxl, be = S.V * S.rho1 + S.rho1 * S.D_l * idxl;
+          const double ga = -S.V * S.rho2 + S.rho2 * S.D_r * idxr, de = -S.rho2 * S.D_r * idxr;
+          S.cu0 = al; S.cu1 = de; S.cu2 = be + al * red1c[KL - 1]; S.cd0 = ga + de * red1c[KL + KR - 1];
+        }
+      }
     }
 
     // ---------------- right-hand side + forward substitution with the resident factors ----------------------------------
-    const int p = n1 - 1, q = rb;
+    const int p = n1 - 1, q = N - 1;         // interface nodes (the right one is the last element of the reversed block)
     const double a_old = C[p], b_old = C[q];
     double c_halo_prev = 0.0, c_halo_next = 0.0;
     if (active) {
-      if (f > 0) c_halo_prev = C[s0 - sdir];
-      c_halo_next = C[s0 + sdir * len];
+      if (f > 0) c_halo_prev = C[s0 - 1];
+      c_halo_next = C[s0 + len];
     }
     __syncthreads();
     double P0 = 0.0, Rp = 0.0, bR = 0.0;
@@ -239,18 +251,18 @@ __global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, co
       double c_prev = c_halo_prev, c_self = C[s0];
       int s = s0;
 #pragma unroll 2
-      for (int k = 0; k < len; ++k, s += sdir) {
-        const double c_next = (k == len - 1) ? c_halo_next : C[s + sdir];
+      for (int k = 0; k < len; ++k, ++s) {
+        const double c_next = (k == len - 1) ? c_halo_next : C[s + 1];
         const double Rn = fma(ML[s], c_prev, fma(MD[s], c_self, fma(MU[s], c_next, -FS[s] * Rp)));
         C[s] = Rn;
         if (mb) P0 = fma(TQ[s], Rn, P0);
         Rp = Rn; c_prev = c_self; c_self = c_next;
       }
       if (len > 1) {
-        int sb = s0 + sdir * (len - 2);
+        int sb = s0 + (len - 2);
         bR = C[sb];
 #pragma unroll 1
-        for (int k = len - 3; k >= 0; --k) { sb -= sdir; bR = C[sb] - FG[sb] * bR; }
+        for (int k = len - 3; k >= 0; --k) { --sb; bR = C[sb] - FG[sb] * bR; }
       }
       exR[tid] = bR;
     }
@@ -266,12 +278,8 @@ __global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, co
     // ---------------- interface condition (set_inner_bc_flux! / _mb! / Dirichlet hold) ----------------------------------
     double aif, bif;
     if (bc == BC_FLUX) {
-      const double idxl = frcp(X[p] - X[p - 1]), idxr = frcp(X[q + 1] - X[q]);
-      const double al = -S.rho1 * S.D_l * idxl, be = S.V * S.rho1 + S.rho1 * S.D_l * idxl;
-      const double ga = -S.V * S.rho2 + S.rho2 * S.D_r * idxr, de = -S.rho2 * S.D_r * idxr;
-      const double U0 = red0[KL - 1], U1 = red1c[KL - 1], W0 = red0[KL + KR - 1], W1 = red1c[KL + KR - 1];
-      const double ca = be + al * U1, cb = ga + de * W1;
-      bif = -(al * U0 + de * W0) / (ca * S.KD + cb);
+      const double al = S.cu0, de = S.cu1, ca = S.cu2, cb = S.cd0;
+      bif = -(al * red0[KL - 1] + de * red0[KL + KR - 1]) / (ca * S.KD + cb);
       aif = S.KD * bif;
     } else if (mb) {
       double v[4] = {0.0, 0.0, 0.0, 0.0};
@@ -284,7 +292,7 @@ __global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, co
       block_sum4<T>(v, S.red);
       const double Vp_ = powd<NDIM>(X[p]), Vq_ = powd<NDIM>(X[q]);
       const double wp = 0.5 * (Vq_ - Vp_) + 0.5 * (Vp_ - powd<NDIM>(X[p - 1]));
-      const double wq = 0.5 * (powd<NDIM>(X[q + 1]) - Vq_) + 0.5 * (Vq_ - Vp_);
+      const double wq = 0.5 * (powd<NDIM>(X[q - 1]) - Vq_) + 0.5 * (Vq_ - Vp_);
       bif = (S.Mass0 - (v[0] + v[2])) / ((v[1] + wp) * S.KD + (v[3] + wq));
       aif = S.KD * bif;
     } else { aif = a_old; bif = b_old; }
@@ -294,23 +302,23 @@ __global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, co
       const double sj = red0[tid] + red1c[tid] * beta;
       const double sp = (jc > 0) ? (red0[tid - 1] + red1c[tid - 1] * beta) : 0.0;
       double cn = sj;
-      int sb = s0 + sdir * (len - 1);
+      int sb = s0 + (len - 1);
       C[sb] = cn;
 #pragma unroll 2
-      for (int k = len - 2; k >= 0; --k) { sb -= sdir; cn = C[sb] - FA[sb] * sp - FG[sb] * cn; C[sb] = cn; }
+      for (int k = len - 2; k >= 0; --k) { --sb; cn = C[sb] - FA[sb] * sp - FG[sb] * cn; C[sb] = cn; }
     }
     if (tid == 0) {
       C[p] = aif; C[q] = bif;
       S.steps += 1;
     }
     __syncthreads();
-    if (tid == 0 && (!isfinite(C[0]) || !isfinite(C[N - 1]) || !isfinite(C[p]))) S.status = 11;
+    if (tid == 0 && (!isfinite(C[0]) || !isfinite(C[rb]) || !isfinite(C[p]))) S.status = 11;     // outer ends, interface
     if ((A.flags & F_RECORD) && A.rec) {
       double v[4] = {0.0, 0.0, 0.0, 0.0};
       for (int i = tid; i < n1 - 1; i += T)
         v[0] += 0.5 * (S.rho1 * powd<NDIM>(X[i + 1]) - S.rho1 * powd<NDIM>(X[i])) * (C[i] + C[i + 1]);
       for (int i = tid; i < n2 - 1; i += T)
-        v[1] += 0.5 * (S.rho2 * powd<NDIM>(X[rb + i + 1]) - S.rho2 * powd<NDIM>(X[rb + i])) * (C[rb + i] + C[rb + i + 1]);
+        v[1] += 0.5 * (S.rho2 * powd<NDIM>(X[N - 2 - i]) - S.rho2 * powd<NDIM>(X[N - 1 - i])) * (C[N - 1 - i] + C[N - 2 - i]);
       block_sum4<T>(v, S.red);
       if (tid == 0 && S.it >= 1 && S.it - 1 < A.rec_cap) {
         double *r = A.rec + ((size_t)mem * (size_t)A.rec_cap + (size_t)(S.it - 1)) * 4;
@@ -324,13 +332,13 @@ __global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, co
   {
     double *gcl = A.C_left + (size_t)mem * A.capL, *gcr = A.C_right + (size_t)mem * A.capR;
     for (int i = tid; i < n1; i += T) gcl[i] = C[i];
-    for (int i = tid; i < n2; i += T) gcr[i] = C[rb + i];
+    for (int i = tid; i < n2; i += T) gcr[i] = C[N - 1 - i];
     if ((A.flags & F_MASS_FINAL) && A.Mass) {
       double v[4] = {0.0, 0.0, 0.0, 0.0};
       for (int i = tid; i < n1 - 1; i += T)
         v[0] += 0.5 * (S.rho1 * powd<NDIM>(X[i + 1]) - S.rho1 * powd<NDIM>(X[i])) * (C[i] + C[i + 1]);
       for (int i = tid; i < n2 - 1; i += T)
-        v[1] += 0.5 * (S.rho2 * powd<NDIM>(X[rb + i + 1]) - S.rho2 * powd<NDIM>(X[rb + i])) * (C[rb + i] + C[rb + i + 1]);
+        v[1] += 0.5 * (S.rho2 * powd<NDIM>(X[N - 2 - i]) - S.rho2 * powd<NDIM>(X[N - 1 - i])) * (C[N - 1 - i] + C[N - 2 - i]);
       block_sum4<T>(v, S.red);
       if (tid == 0) A.Mass[mem] = v[0] + v[1];
     }
