@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, co
   __shared__ double redS[T], redD[T], redU[T], red0[T], red1[T];
   __shared__ double exA[T], exG[T], exR[T];
   __shared__ double red1c[T];                // solution of the reduced system for the interface-unknown column (matrix-only)
+  __shared__ double rfac[RFAC_N(T) * 32];    // matrix part of the reduced solve (reduced_factor), redone per factorisation
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int mem = member0 + blockIdx.x;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, co
       if (active) { redS[tid] = r_s; redD[tid] = 1.0; redU[tid] = lastChunk ? 0.0 : r_u; red0[tid] = 0.0; red1[tid] = lastChunk ? -r_Gp : 0.0; }
       else { redS[tid] = 0.0; redD[tid] = 1.0; redU[tid] = 0.0; red0[tid] = 0.0; red1[tid] = 0.0; }
       __syncthreads();
-      if (tid < 32) reduced_solve<T, 2>(redS, redD, redU, red0, red1);
+      if (tid < 32) { reduced_solve<T, 2>(redS, redD, redU, red0, red1); reduced_factor<T>(redS, redD, redU, rfac); }
       __syncthreads();
       red1c[tid] = red1[tid];
       if (bc == BC_FLUX) {
@@ -267,12 +268,11 @@ __global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, co
       exR[tid] = bR;
     }
     __syncthreads();
-    if (active) {
-      if (!lastChunk) { redS[tid] = r_s; redD[tid] = 1.0; redU[tid] = r_u; red0[tid] = (Rp - r_Gp * exR[tid + 1]) * r_inv; }
-      else { redS[tid] = r_s; redD[tid] = 1.0; redU[tid] = 0.0; red0[tid] = Rp; }
-    } else { redS[tid] = 0.0; redD[tid] = 1.0; redU[tid] = 0.0; red0[tid] = 0.0; }
+    // right-hand side of the reduced system; its matrix part was factorised with the step matrix (reduced_factor)
+    if (active) red0[tid] = lastChunk ? Rp : (Rp - r_Gp * exR[tid + 1]) * r_inv;
+    else red0[tid] = 0.0;
     __syncthreads();
-    if (tid < 32) reduced_solve<T, 1>(redS, redD, redU, red0, red1);
+    if (tid < 32) reduced_apply<T>(rfac, red0);
     __syncthreads();
 
     // ---------------- interface condition (set_inner_bc_flux! / _mb! / Dirichlet hold) ----------------------------------

@@ -701,6 +701,102 @@ __device__ __forceinline__ void reduced_solve(double *rs, double *rd, double *ru
   }
 }
 
+// ---- the same solve split in a matrix part and a right-hand-side part (fixed-interface kernel: the reduced matrix
+// only changes with the factorisation).  reduced_factor stores, per lane, everything of reduced_solve that does not
+// depend on the right-hand side (RFAC_N(T) coefficients per lane, fac[c*32 + lane]); reduced_apply then needs two
+// operations per row and three per PCR level, with the same operations on the right-hand side, in the same order, as
+// reduced_solve<T, 1> (bit-identical solution).  Both are called by warp 0 only.
+__host__ __device__ constexpr int RFAC_N(int T) { return 4 * (T / 32) + 17; }
+template <int T>
+__device__ __forceinline__ void reduced_factor(const double *rs, const double *rd, const double *ru, double *fac) {
+  constexpr int RPL = T / 32;
+  const int lane = threadIdx.x;
+  const int g0 = lane * RPL;
+  double A[RPL], G[RPL];
+  int c = 0;
+  auto put = [&](double v) { fac[c * 32 + lane] = v; ++c; };
+  {
+    double inv = frcp_(rd[g0]);
+    A[0] = rs[g0] * inv; G[0] = ru[g0] * inv;
+    put(0.0); put(inv);                                   // sb, inv of row 0 (sb unused: no previous row)
+#pragma unroll
+    for (int k = 1; k < RPL; ++k) {
+      const int g = g0 + k;
+      const double sb = rs[g];
+      inv = frcp_(rd[g] - sb * G[k - 1]);
+      A[k] = -sb * A[k - 1] * inv;
+      G[k] = ru[g] * inv;
+      put(sb); put(inv);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < RPL; ++k) { put(A[k]); put(G[k]); }
+  double bA = 0.0, bG = -1.0;
+  if (RPL > 1) {
+    bA = A[RPL - 2]; bG = G[RPL - 2];
+#pragma unroll
+    for (int k = RPL - 3; k >= 0; --k) { const double Gk = G[k]; bA = A[k] - Gk * bA; bG = -Gk * bG; }
+  }
+  const double nA = __shfl_down_sync(0xffffffffu, bA, 1), nG = __shfl_down_sync(0xffffffffu, bG, 1);
+  double ps, pu;
+  {
+    const double Gl = (lane == 31) ? 0.0 : G[RPL - 1];
+    const double inv = frcp_(1.0 - Gl * nA);
+    ps = A[RPL - 1] * inv;
+    pu = -Gl * nG * inv;
+    if (lane == 31) pu = 0.0;
+    if (lane == 0) ps = 0.0;
+    put(Gl); put(inv);
+  }
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    double ls = __shfl_up_sync(0xffffffffu, ps, d), lu = __shfl_up_sync(0xffffffffu, pu, d);
+    double hs = __shfl_down_sync(0xffffffffu, ps, d), hu = __shfl_down_sync(0xffffffffu, pu, d);
+    if (lane < d) { ls = 0.0; lu = 0.0; }
+    if (lane + d > 31) { hs = 0.0; hu = 0.0; }
+    const double inv = frcp_(1.0 - ps * lu - pu * hs);
+    put((lane < d) ? 0.0 : ps); put((lane + d > 31) ? 0.0 : pu); put(inv);     // masked: the neighbour does not exist
+    const double ns = -ps * ls * inv, nu = -pu * hu * inv;
+    ps = ns; pu = nu;
+  }
+}
+template <int T>
+__device__ __forceinline__ void reduced_apply(const double *fac, double *r0) {
+  constexpr int RPL = T / 32;
+  const int lane = threadIdx.x;
+  const int g0 = lane * RPL;
+  const double *f = fac + lane;
+  double R0[RPL];
+  R0[0] = r0[g0] * f[1 * 32];
+#pragma unroll
+  for (int k = 1; k < RPL; ++k) R0[k] = (r0[g0 + k] - f[(2 * k) * 32] * R0[k - 1]) * f[(2 * k + 1) * 32];
+  const double *fa = f + 2 * RPL * 32;                    // A[k], G[k] pairs
+  double bR0 = 0.0;
+  if (RPL > 1) {
+    bR0 = R0[RPL - 2];
+#pragma unroll
+    for (int k = RPL - 3; k >= 0; --k) bR0 = R0[k] - fa[(2 * k + 1) * 32] * bR0;
+  }
+  const double nR0 = __shfl_down_sync(0xffffffffu, bR0, 1);
+  const double *fl = f + 4 * RPL * 32;                    // Gl, inv of the level-3 row, then (ps, pu, inv) per PCR level
+  double p0 = (R0[RPL - 1] - fl[0] * nR0) * fl[32];
+  int c = 2;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1, c += 3) {
+    const double l0 = __shfl_up_sync(0xffffffffu, p0, d), h0 = __shfl_down_sync(0xffffffffu, p0, d);
+    p0 = (p0 - fl[c * 32] * l0 - fl[(c + 1) * 32] * h0) * fl[(c + 2) * 32];
+  }
+  double sp0 = __shfl_up_sync(0xffffffffu, p0, 1);
+  if (lane == 0) sp0 = 0.0;
+  double c0 = p0;
+  r0[g0 + RPL - 1] = c0;
+#pragma unroll
+  for (int k = RPL - 2; k >= 0; --k) {
+    c0 = R0[k] - fa[(2 * k) * 32] * sp0 - fa[(2 * k + 1) * 32] * c0;
+    r0[g0 + k] = c0;
+  }
+}
+
 // ======================================================================================================
 // The kernel
 // ======================================================================================================
