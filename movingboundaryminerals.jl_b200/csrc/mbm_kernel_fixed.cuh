@@ -16,8 +16,14 @@
 
 namespace mbm {
 
+// resident warps per SM the register allocation is sized for: 16 = 128 registers per thread (the nine arrays of config 3
+// leave room for four 128-thread CTAs anyway; with 24 warps = 80 registers the compiler re-derived the array
+// addresses inside every row loop)
+#ifndef MBM_FIXED_WARPS
+#define MBM_FIXED_WARPS 16
+#endif
 template <int T, int NDIM>
-__global__ void __launch_bounds__(T, 768 / T) mbm_fixed_kernel(const KArgs A, const int member0) {
+__global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(const KArgs A, const int member0) {
   extern __shared__ double smem[];
   __shared__ Scal S;
   __shared__ double redS[T], redD[T], redU[T], red0[T], red1[T];
