@@ -276,11 +276,12 @@ void v2_plan(int capL, int capR, int smem_per_sm, int ndim, int *T2, int *kS) {
   ks_max -= ks_max % 8;
   if (ks > ks_max) ks = ks_max;
   int T = 256;
-  if (ks <= 9 * 64) T = 64;
+  if (ks <= 9 * 32) T = 32;                // one warp per member: every block barrier is a warp barrier
+  else if (ks <= 9 * 64) T = 64;
   else if (ks <= 9 * 128) T = 128;
   if (const char *e = getenv("MBM_V2_THREADS")) {
     const int t = atoi(e);
-    if (t == 64 || t == 128 || t == 256) T = t;
+    if (t == 32 || t == 64 || t == 128 || t == 256) T = t;
   }
 #if defined(MBM_DEV_MIN) && MBM_V2_T != 256
   if (T == 256) { *T2 = MBM_V2_T; *kS = ks; return; }      // the launch switch maps "256" to the MBM_V2_T instantiation
@@ -373,6 +374,7 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
       mbm::KArgs A2 = A;
       A2.only_deferred = 0;
       switch (T2) {
+        case 32: rc = launch_v2_T<32>(A2, m0 + off, n, dyn2, s); break;
         case 64: rc = launch_v2_T<64>(A2, m0 + off, n, dyn2, s); break;
         case 128: rc = launch_v2_T<128>(A2, m0 + off, n, dyn2, s); break;
         default: rc = launch_v2_T<256>(A2, m0 + off, n, dyn2, s); break;

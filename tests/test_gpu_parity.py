@@ -199,8 +199,8 @@ def test_handover_to_general_kernel(oracle, cuda_lib, monkeypatch):
 
 
 def test_tuned_kernel_thread_configs(oracle, cuda_lib, monkeypatch):
-    """the tuned kernel at 64/128/256 threads per member"""
-    for t in ("64", "128", "256"):
+    """the tuned kernel at 32/64/128/256 threads per member"""
+    for t in ("32", "64", "128", "256"):
         monkeypatch.setenv("MBM_V2_THREADS", t)
         pars = []
         for V, res in ((-1e-7, [60, 90]), (1e-7, [100, 150]), (3e-8, [33, 70])):
