@@ -267,7 +267,7 @@ int v2_static_T(int ndim) {
   }
 #endif
 }
-void v2_plan(int capL, int capR, int smem_per_sm, int ndim, int *T2, int *kS) {
+void v2_plan(int capL, int capR, int nmax_hint, int smem_per_sm, int ndim, int *T2, int *kS) {
   int ks = capL + capR + 1;
   if (const char *e = getenv("MBM_KCAP")) { const int a = atoi(e); if (a >= 8 && a < ks) ks = a; }
   const int stat = v2_static_T<256>(ndim) + 64;          // the widest instantiation bounds the others
@@ -275,10 +275,13 @@ void v2_plan(int capL, int capR, int smem_per_sm, int ndim, int *T2, int *kS) {
   int ks_max = per_cta / (4 * 8);
   ks_max -= ks_max % 8;
   if (ks > ks_max) ks = ks_max;
+  // threads per member from the node counts when the host knows them (host buffers: largest n1 + n2 of the shard, with
+  // room to grow by a quarter), else from the capacities; a member that outgrows 9*T nodes per phase is handed over
+  const int nsz = (nmax_hint > 0 && nmax_hint + nmax_hint / 4 + 2 < ks) ? (nmax_hint + nmax_hint / 4 + 2) : ks;
   int T = 256;
-  if (ks <= 9 * 32) T = 32;                // one warp per member: every block barrier is a warp barrier
-  else if (ks <= 9 * 64) T = 64;
-  else if (ks <= 9 * 128) T = 128;
+  if (nsz <= 9 * 32) T = 32;               // one warp per member: every block barrier is a warp barrier
+  else if (nsz <= 9 * 64) T = 64;
+  else if (nsz <= 9 * 128) T = 128;
   if (const char *e = getenv("MBM_V2_THREADS")) {
     const int t = atoi(e);
     if (t == 32 || t == 64 || t == 128 || t == 256) T = t;
@@ -333,7 +336,7 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
   if (use_v2) {
     int smem_sm = 0;
     CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
-    v2_plan(A.capL, A.capR, smem_sm, A.ndim, &T2, &A.kcapL);
+    v2_plan(A.capL, A.capR, A.pad3_, smem_sm, A.ndim, &T2, &A.kcapL);
     if (A.kcapL < 8) use_v2 = false;
   }
   if (couple_pv && !getenv("MBM_NO_CHAIN")) {

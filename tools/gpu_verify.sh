@@ -10,3 +10,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:mbm_step_kernel_v2 -c 1 -f -o gpurun_out/prof_v2_head \
   python bench.py --steps 1 --warmup 0 --no-cpu --no-e2e > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; tail -1 gpurun_out/bench_full.log | cut -c1-400
+python tools/measure_configs.py > gpurun_out/configs.log 2>&1; tail -4 gpurun_out/configs.log | cut -c1-250
