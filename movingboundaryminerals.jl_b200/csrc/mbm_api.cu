@@ -300,7 +300,10 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
   const int capS = A.capS;
   const size_t per_cta = 5 * (size_t)capS + (size_t)(capS / 256 + 8);
   const size_t dyn = per_cta * sizeof(double);
-  int T = threads_for(capS);
+  // threads per member from the shard's largest node count when the host knows it (with room to grow), else from the
+  // capacities: the capacities of small members are several times their node counts
+  const int nsz = (A.pad3_ > 0 && 2 * A.pad3_ + 8 < capS) ? (2 * A.pad3_ + 8) : capS;
+  int T = threads_for(nsz);
   int maxOptin = 0;
   CK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   bool use_global = (dyn + static_smem_for(T) > (size_t)maxOptin);

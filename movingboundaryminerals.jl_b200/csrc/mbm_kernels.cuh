@@ -801,7 +801,8 @@ __device__ __forceinline__ void reduced_apply(const double *fac, double *r0) {
 // The kernel
 // ======================================================================================================
 template <int T>
-__global__ void __launch_bounds__(T) mbm_step_kernel(const KArgs A, const int member0) {
+// small members (one or two warps each) are latency-bound serial code: size the registers for 16 resident warps per SM
+__global__ void __launch_bounds__(T, (T <= 64) ? 512 / T : 1) mbm_step_kernel(const KArgs A, const int member0) {
   extern __shared__ double smem[];
   __shared__ Scal S;
   __shared__ double redS[T], redD[T], redU[T], red0[T], red1[T];   // reduced system
