@@ -320,3 +320,25 @@ def test_D1_material_law(oracle, cuda_lib):
             assert _relerr(a, b) < 2e-9
     assert _relerr(eo.Ri, eg.Ri) < 1e-10
     assert _relerr(eo.last[:, :2], eg.last[:, :2]) < 1e-12       # D_l, D_r of the last step
+
+
+def test_pieces_staggered_equal_single_piece(cuda_lib, monkeypatch):
+    """host-buffer calls cut into pieces on their own streams (input copies staggered piece by piece, as large shards are
+    by default) return the same bits as one piece, with and without the staggering"""
+    pars = []
+    for k in range(37):                           # not a multiple of the piece count: the last piece is short
+        p = d.pars_MB_growth(); p.update(V_ip=(-1e-7 if k % 2 else 1e-7) * (1.0 + 0.01 * k), res=[60 + k, 90 + k])
+        pars.append(p)
+    e0, _ = d.build_couple_ensemble(pars, cuda_lib)
+    runs = []
+    for pieces, nostagger in (("1", None), ("4", None), ("8", None), ("4", "1")):
+        monkeypatch.setenv("MBM_PIECES", pieces)
+        if nostagger: monkeypatch.setenv("MBM_NO_STAGGER", nostagger)
+        else: monkeypatch.delenv("MBM_NO_STAGGER", raising=False)
+        e = e0.copy()
+        assert e.run(cuda_lib, max_steps=60, flags=abi.FLAG_MASS_FINAL) == 0
+        assert np.all(e.status == 0)
+        runs.append(e)
+    for k in ("x_left", "C_left", "x_right", "C_right", "res", "it", "Ri", "t", "idx_hash", "Mass", "node_steps"):
+        for r in runs[1:]:
+            assert np.array_equal(runs[0].arrays[k], r.arrays[k]), k
