@@ -153,7 +153,9 @@ class CoupleEnsemble:
                   "newton_R", "last"):
             setattr(io, n, abi.dptr(a[n]))
         io.res = abi.i64ptr(a["res"]); io.it = abi.i64ptr(a["it"]); io.node_steps = abi.i64ptr(a["node_steps"])
-        io.status = abi.i32ptr(a["status"]); io.warn = abi.i32ptr(a["warn"]); io.idx_hash = abi.u64ptr(a["idx_hash"])
+        io.status = abi.i32ptr(a["status"]); io.warn = abi.i32ptr(a["warn"])
+        if a["idx_hash"] is not None:                     # optional output: None = no regrid checksum (NULL in the ABI)
+            io.idx_hash = abi.u64ptr(a["idx_hash"])
         if rec_cap > 0:
             if a["rec"] is None or a["rec"].shape != (self.M, rec_cap, 4):
                 a["rec"] = np.zeros((self.M, rec_cap, 4), dtype=np.float64)

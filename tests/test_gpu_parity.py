@@ -342,3 +342,19 @@ def test_pieces_staggered_equal_single_piece(cuda_lib, monkeypatch):
     for k in ("x_left", "C_left", "x_right", "C_right", "res", "it", "Ri", "t", "idx_hash", "Mass", "node_steps"):
         for r in runs[1:]:
             assert np.array_equal(runs[0].arrays[k], r.arrays[k]), k
+
+
+def test_checksum_is_optional_and_does_not_change_values(cuda_lib):
+    """io.idx_hash = NULL (what bench.py passes) selects the pchip transfer compiled without the checksum bookkeeping:
+    every other output must be bit-identical to a run with the checksum"""
+    pars = []
+    for V, res in ((-1e-7, [100, 150]), (1e-7, [100, 150]), (-2e-7, [60, 90]), (5e-8, [130, 131])):
+        p = d.pars_MB_growth(); p.update(V_ip=V, res=res); pars.append(p)
+    e0, _ = d.build_couple_ensemble(pars, cuda_lib)
+    ea, eb = e0.copy(), e0.copy()
+    eb.arrays["idx_hash"] = None
+    assert ea.run(cuda_lib, max_steps=300, flags=abi.FLAG_MASS_FINAL) == 0
+    assert eb.run(cuda_lib, max_steps=300, flags=abi.FLAG_MASS_FINAL) == 0
+    assert np.all(ea.status == 0) and np.all(eb.status == 0)
+    for k in ("x_left", "C_left", "x_right", "C_right", "res", "it", "Ri", "t", "Mass", "node_steps"):
+        assert np.array_equal(ea.arrays[k], eb.arrays[k]), k
