@@ -257,13 +257,25 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
     if (active) {
       double c_prev = c_halo_prev, c_self = C[s0];
       int s = s0;
+      // (two copies of the loop: the mass-balance functional is only accumulated for inner_bc = mb, and a test of a
+      //  kernel parameter inside the loop is re-read from the constant bank every row)
+      if (mb) {
 #pragma unroll 2
-      for (int k = 0; k < len; ++k, ++s) {
-        const double c_next = (k == len - 1) ? c_halo_next : C[s + 1];
-        const double Rn = fma(ML[s], c_prev, fma(MD[s], c_self, fma(MU[s], c_next, -FS[s] * Rp)));
-        C[s] = Rn;
-        if (mb) P0 = fma(TQ[s], Rn, P0);
-        Rp = Rn; c_prev = c_self; c_self = c_next;
+        for (int k = 0; k < len; ++k, ++s) {
+          const double c_next = (k == len - 1) ? c_halo_next : C[s + 1];
+          const double Rn = fma(ML[s], c_prev, fma(MD[s], c_self, fma(MU[s], c_next, -FS[s] * Rp)));
+          C[s] = Rn;
+          P0 = fma(TQ[s], Rn, P0);
+          Rp = Rn; c_prev = c_self; c_self = c_next;
+        }
+      } else {
+#pragma unroll 2
+        for (int k = 0; k < len; ++k, ++s) {
+          const double c_next = (k == len - 1) ? c_halo_next : C[s + 1];
+          const double Rn = fma(ML[s], c_prev, fma(MD[s], c_self, fma(MU[s], c_next, -FS[s] * Rp)));
+          C[s] = Rn;
+          Rp = Rn; c_prev = c_self; c_self = c_next;
+        }
       }
       if (len > 1) {
         int sb = s0 + (len - 2);

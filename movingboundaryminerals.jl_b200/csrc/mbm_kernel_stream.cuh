@@ -81,11 +81,11 @@ __device__ __noinline__ double end_slope3(PPt Pe, PPt Pa, PPt Pb) {
   return d;
 }
 
-template <int T>
+template <int T, bool do_hash>
 __device__ __forceinline__ void pchip_run_stream(const double *X, const double *C, const StreamLayout &L, const int phase,
                                                  const int n, const int nn, const double lr_a, const double lr_b,
                                                  double *Xn, double *Cn, const int idx0, const int cnt,
-                                                 const bool do_hash, const long long it, unsigned long long &hash) {
+                                                 const long long it, unsigned long long &hash) {
   const int tid = threadIdx.x;
   const bool MIR = (phase != 0);                      // runtime: both phases run one instruction stream
   const double sg = MIR ? -1.0 : 1.0;
@@ -510,7 +510,8 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream_kernel(const KA
       const int idx0 = ncol * LN.m;
       const int cnt = max(0, min(idx0 + LN.m, nn) - idx0);
       if (cnt > 0) {
-        pchip_run_stream<T>(X, C, L, nblk, no, nn, nblk ? Ri1 : 0.0, nblk ? Ri2 : Ri1, Xn, Cn, idx0, cnt, do_hash, S.it, hash_local);
+        if (do_hash) pchip_run_stream<T, true>(X, C, L, nblk, no, nn, nblk ? Ri1 : 0.0, nblk ? Ri2 : Ri1, Xn, Cn, idx0, cnt, S.it, hash_local);
+        else pchip_run_stream<T, false>(X, C, L, nblk, no, nn, nblk ? Ri1 : 0.0, nblk ? Ri2 : Ri1, Xn, Cn, idx0, cnt, 0, hash_local);
       }
     }
     __threadfence_block();

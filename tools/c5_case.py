@@ -9,6 +9,7 @@ M = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 res = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
 ens, _ = d.build_couple_ensemble(E.c5_highres(M, res, max_steps=100), lib, cap_left=res + 4, cap_right=res + 4)
+if os.environ.get('NOHASH'): ens.arrays['idx_hash'] = None
 ens.run(lib, max_steps=2)
 n0 = int(ens.node_steps.sum())
 for rep in range(2):
