@@ -26,7 +26,7 @@ template <int T, int NDIM>
 __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(const KArgs A, const int member0) {
   extern __shared__ double smem[];
   __shared__ Scal S;
-  __shared__ double redS[T], redD[T], redU[T], red0[T], red1[T];
+  __shared__ double redS[T], redD[T], redU[T], red0[T + 32], red1[T];   // red0: per-step right-hand side, skewed (red_ix)
   __shared__ double exA[T], exG[T], exR[T];
   __shared__ double red1c[T];                // solution of the reduced system for the interface-unknown column (matrix-only)
   __shared__ double rfac[RFAC_N(T) * 32];    // matrix part of the reduced solve (reduced_factor), redone per factorisation
@@ -287,23 +287,24 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
     }
     __syncthreads();
     // right-hand side of the reduced system; its matrix part was factorised with the step matrix (reduced_factor)
-    if (active) red0[tid] = lastChunk ? Rp : (Rp - r_Gp * exR[tid + 1]) * r_inv;
-    else red0[tid] = 0.0;
+    const int rix = red_ix<T>(tid), rixm = red_ix<T>(tid > 0 ? tid - 1 : 0);
+    if (active) red0[rix] = lastChunk ? Rp : (Rp - r_Gp * exR[tid + 1]) * r_inv;
+    else red0[rix] = 0.0;
     __syncthreads();
-    if (tid < 32) reduced_apply<T>(rfac, red0);
+    if (tid < 32) reduced_apply<T, true>(rfac, red0);
     __syncthreads();
 
     // ---------------- interface condition (set_inner_bc_flux! / _mb! / Dirichlet hold) ----------------------------------
     double aif, bif;
     if (bc == BC_FLUX) {
       const double al = S.cu0, de = S.cu1, ca = S.cu2, cb = S.cd0;
-      bif = -(al * red0[KL - 1] + de * red0[KL + KR - 1]) / (ca * S.KD + cb);
+      bif = -(al * red0[red_ix<T>(KL - 1)] + de * red0[red_ix<T>(KL + KR - 1)]) * frcp(ca * S.KD + cb);
       aif = S.KD * bif;
     } else if (mb) {
       double v[4] = {0.0, 0.0, 0.0, 0.0};
       if (active) {
-        const double s0v = red0[tid], s1v = red1c[tid];
-        const double q0 = (jc > 0) ? red0[tid - 1] : 0.0, q1 = (jc > 0) ? red1c[tid - 1] : 0.0;
+        const double s0v = red0[rix], s1v = red1c[tid];
+        const double q0 = (jc > 0) ? red0[rixm] : 0.0, q1 = (jc > 0) ? red1c[tid - 1] : 0.0;
         const double c0 = P0 + cQa * q0 + cQc * s0v, c1 = cQa * q1 + cQc * s1v;
         if (blk == 0) { v[0] = c0; v[1] = c1; } else { v[2] = c0; v[3] = c1; }
       }
@@ -311,14 +312,14 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
       const double Vp_ = powd<NDIM>(X[p]), Vq_ = powd<NDIM>(X[q]);
       const double wp = 0.5 * (Vq_ - Vp_) + 0.5 * (Vp_ - powd<NDIM>(X[p - 1]));
       const double wq = 0.5 * (powd<NDIM>(X[q - 1]) - Vq_) + 0.5 * (Vq_ - Vp_);
-      bif = (S.Mass0 - (v[0] + v[2])) / ((v[1] + wp) * S.KD + (v[3] + wq));
+      bif = (S.Mass0 - (v[0] + v[2])) * frcp((v[1] + wp) * S.KD + (v[3] + wq));
       aif = S.KD * bif;
     } else { aif = a_old; bif = b_old; }
     // ---------------- back-substitution -----------------------------------------------------------------------------------
     if (active) {
       const double beta = blk ? bif : aif;
-      const double sj = red0[tid] + red1c[tid] * beta;
-      const double sp = (jc > 0) ? (red0[tid - 1] + red1c[tid - 1] * beta) : 0.0;
+      const double sj = red0[rix] + red1c[tid] * beta;
+      const double sp = (jc > 0) ? (red0[rixm] + red1c[tid - 1] * beta) : 0.0;
       double cn = sj;
       int sb = s0 + (len - 1);
       C[sb] = cn;

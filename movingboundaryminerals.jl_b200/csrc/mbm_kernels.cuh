@@ -625,11 +625,18 @@ __device__ __forceinline__ double pchip_eval_otf(const double *x, const double *
 
 // ---- reduced-system solve (levels 2 and 3): warp 0 solves the T-row tridiagonal system with two right-
 // hand sides held in shared memory (rs: sub, rd: diag, ru: sup, r0, r1); solution overwrites r0, r1.
-template <int T, int NRHS = 2>
+// SKEW: row g is stored at red_ix<T>(g) = g + g / RPL (arrays of T + 32 entries): the lanes of warp 0 then read their
+// chunks with an odd stride (RPL + 1 doubles) instead of RPL = 2, 4 or 8 doubles, i.e. without bank conflicts.
+template <int T>
+__device__ __forceinline__ int red_ix(int g) {
+  constexpr int RPL = T / 32;
+  return (RPL > 1) ? g + g / RPL : g;
+}
+template <int T, int NRHS = 2, bool SKEW = false>
 __device__ __forceinline__ void reduced_solve(double *rs, double *rd, double *ru, double *r0, double *r1) {
   constexpr int RPL = T / 32;
   const int lane = threadIdx.x;  // caller guarantees threadIdx.x < 32
-  const int g0 = lane * RPL;
+  const int g0 = (SKEW && RPL > 1) ? lane * (RPL + 1) : lane * RPL;     // chunk rows are contiguous either way
   double A[RPL], G[RPL], R0[RPL], R1[RPL];
   // forward pass: every row of the lane's chunk in terms of the previous separator and the next row
   {
@@ -760,11 +767,11 @@ __device__ __forceinline__ void reduced_factor(const double *rs, const double *r
     ps = ns; pu = nu;
   }
 }
-template <int T>
+template <int T, bool SKEW = false>
 __device__ __forceinline__ void reduced_apply(const double *fac, double *r0) {
   constexpr int RPL = T / 32;
   const int lane = threadIdx.x;
-  const int g0 = lane * RPL;
+  const int g0 = (SKEW && RPL > 1) ? lane * (RPL + 1) : lane * RPL;       // SKEW: r0 indexed by red_ix<T>
   const double *f = fac + lane;
   double R0[RPL];
   R0[0] = r0[g0] * f[1 * 32];
