@@ -202,7 +202,10 @@ int launch_fixed_T(const mbm::KArgs &A, int member0, int count, size_t smem_byte
 }
 template <int NDIM>
 int launch_stream_N(const mbm::KArgs &A, int member0, int count, cudaStream_t s) {
-  mbm::mbm_stream_kernel<256, NDIM><<<count, 256, 0, s>>>(A, member0);
+  auto kern = mbm::mbm_stream_kernel<256, NDIM>;
+  if (int rc = launch_rc("streaming kernel: shared-memory opt-in",
+                         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mbm::STG_BYTES))) return rc;
+  kern<<<count, 256, mbm::STG_BYTES, s>>>(A, member0);
   return launch_rc("streaming kernel launch", cudaGetLastError());
 }
 int launch_stream(const mbm::KArgs &A, int member0, int count, cudaStream_t s) {

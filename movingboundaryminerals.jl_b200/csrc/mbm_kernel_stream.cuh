@@ -11,20 +11,57 @@
 //   regrid          read x, C (walking window)   write x_new, C_new (in the next step's layout)
 // Both phases look the same in this layout: the left phase is stored by node index, the right phase by REVERSED node
 // index, so "towards the interface" is "k increasing" for both and the node the interface advection inserts
-// (functions.jl:33-35 / :46-48) is an append in either case.  The roofline that bounds this kernel is HBM:
-// algorithmic 32 B per node-step; this implementation moves ~128 B per node-step.
+// (functions.jl:33-35 / :46-48) is an append in either case.  A CTA's row k of an array is one contiguous 2 KB block:
+// the forward sweep and the back-substitution stream their rows through shared memory with 1-D bulk copies
+// (cp.async.bulk + mbarrier, batches of STG_R rows issued one batch ahead by thread 0), the regrid walk reads through
+// L1 with a software prefetch.  The roofline that bounds this kernel is HBM: algorithmic 32 B per node-step
+// (SURVEY.md §8(d)); this implementation moves 104 B per node-step.
 #pragma once
 #include "mbm_kernel_fixed.cuh"
 
 namespace mbm {
 
 #ifndef MBM_SPF
-#define MBM_SPF 8
+#define MBM_SPF 4
 #endif
 #ifndef MBM_STREAM_MINB
 #define MBM_STREAM_MINB 2
 #endif
-constexpr int SPF = MBM_SPF;   // software prefetch distance of the column sweeps, in rows (one row of a CTA = 2 KB per array)
+constexpr int SPF = MBM_SPF;   // software prefetch distance of the regrid walk, in rows (one row of a CTA = 2 KB per array)
+
+// ---- bulk-copy (TMA) row staging: a CTA's row k of an array (element k of all T columns) is one contiguous 2 KB
+// block, so the column sweeps stream their rows through shared memory with 1-D bulk copies (cp.async.bulk, completion on
+// an mbarrier) instead of per-thread loads: batches of STG_R rows, STG_NBF / STG_NBB batches resident for the forward
+// sweep (2 arrays) / the back-substitution (3 arrays), issued by thread 0 one batch ahead of the one being consumed.
+#ifndef MBM_STG_R
+#define MBM_STG_R 7
+#endif
+constexpr int STG_R = MBM_STG_R, STG_NBF = 3, STG_NBB = 2;
+constexpr int STG_BYTES = STG_R * STG_NBF * 2 * 256 * 8;            // = STG_R * STG_NBB * 3 * 256 * 8 = 86016
+static_assert(STG_R * STG_NBB * 3 * 256 * 8 == STG_BYTES, "forward and backward staging share one allocation");
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 struct StreamLayout {
   int m;        // nodes per column
@@ -195,10 +232,17 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream_kernel(const KA
   __shared__ double redS[T], redD[T], redU[T], red0[T], red1[T];
   __shared__ double exA[T], exG[T], exR[T];
   __shared__ StreamLayout Lcur, Lnew;
+  extern __shared__ __align__(128) double stg[];                 // STG_BYTES of row staging
+  __shared__ __align__(8) unsigned long long fullb[STG_NBF];
+  unsigned stg_par = 0;                                          // parity bit of every staging barrier (uniform)
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int mem = member0 + blockIdx.x;
   if (mem >= A.M) return;
+  if (tid == 0) {
+    for (int b = 0; b < STG_NBF; ++b) mbar_init(&fullb[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   const int MC = A.kcapL;                     // rows per column capacity of the workspace
   const size_t ASZ = (size_t)MC * T;
   double *base = A.workspace + (size_t)blockIdx.x * 6 * ASZ;
@@ -377,8 +421,9 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream_kernel(const KA
       if (f > 0) { x_halo_prev = X[paddr(T, L, blk, f - 1)]; c_halo_prev = C[paddr(T, L, blk, f - 1)]; }
       x_halo_next = X[paddr(T, L, blk, f + len)]; c_halo_next = C[paddr(T, L, blk, f + len)];
     }
+    fence_proxy_async();                      // the rows were written with ordinary stores (regrid, node insertion)
     __syncthreads();
-    if (active) {
+    {                                         // all threads (a column without rows has len == 0)
       // forward sweep over the column (coalesced: element k of column t at k*T + t), same row arithmetic as the tuned
       // resident kernel (direction-agnostic element matrices, combined element carry).  The first row of the column
       // in terms of the two separators, C_0 = bR - bA*s_prev - bG*s_own, is accumulated on the way
@@ -396,18 +441,9 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream_kernel(const KA
         if (mb) hprev = 0.5 * fabs(Vs - powd<NDIM>(x_halo_prev));
       }
       bA = 0.0; bR = 0.0;
-      for (int d = 1; d < SPF && d < len; ++d) {                         // warm the first rows
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(X + a + (size_t)d * T));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(C + a + (size_t)d * T));
-      }
-#pragma unroll 2
-      for (int k = 0; k < len; ++k, a += T) {
+      // one row of the sweep (k: row of the column, a = k*T + tid), given the next node's x and C
+      auto fwd_row = [&](const int k, const size_t a, const double x_next, const double c_next) {
         const bool last = (k == len - 1);
-        if (k + SPF < len) {
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(X + a + (size_t)SPF * T));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(C + a + (size_t)SPF * T));
-        }
-        const double x_next = last ? x_halo_next : X[a + T], c_next = last ? c_halo_next : C[a + T];
         double Aself, A12, Anext, kk;
         elem_mats_dir<NDIM>(x_self, x_next, Dsd, idts, Aself, A12, Anext, kk);
         double diag = (Aself - kk) + dcar;
@@ -432,9 +468,42 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream_kernel(const KA
         Ap = An; Gp = Gn; Rp = Rn;
         dcar = Anext - kk; rcar = fma(A12, c_self, Anext * c_next); sub = sup_true;
         x_self = x_next; c_self = c_next;
+      };
+      // rows 1 .. m-1 (the "next" rows of iterations 0 .. m-2) come through shared memory in batches of STG_R rows;
+      // iteration len-1 of every column uses its halo instead
+      {
+        const int nrows = m - 1, nbatch = (nrows + STG_R - 1) / STG_R;
+        auto issue = [&](const int b) {       // thread 0: rows 1 + b*R .. of x and C into buffer b % NBF
+          const int r0 = 1 + b * STG_R, nr = min(STG_R, nrows - b * STG_R), buf = b % STG_NBF;
+          const unsigned bytes = (unsigned)nr * T * 8u;
+          double *dst = stg + (size_t)buf * (2 * STG_R * T);
+          mbar_expect_tx(&fullb[buf], 2u * bytes);
+          bulk_g2s(dst, X + (size_t)r0 * T, bytes, &fullb[buf]);
+          bulk_g2s(dst + STG_R * T, C + (size_t)r0 * T, bytes, &fullb[buf]);
+        };
+        if (tid == 0) for (int b = 0; b < STG_NBF - 1 && b < nbatch; ++b) issue(b);
+        for (int b = 0; b < nbatch; ++b) {
+          const int buf = b % STG_NBF;
+          if (tid == 0 && b + STG_NBF - 1 < nbatch) issue(b + STG_NBF - 1);     // into the buffer freed by batch b-1
+          mbar_wait(&fullb[buf], (stg_par >> buf) & 1u);
+          stg_par ^= 1u << buf;
+          const double *xs_ = stg + (size_t)buf * (2 * STG_R * T) + tid, *cs_ = xs_ + STG_R * T;
+          const int k0 = b * STG_R, nr = min(STG_R, nrows - k0);
+#pragma unroll 1
+          for (int rr = 0; rr < nr; ++rr) {
+            const int k = k0 + rr;
+            if (k < len) {
+              const bool last = (k == len - 1);
+              fwd_row(k, (size_t)k * T + tid, last ? x_halo_next : xs_[rr * T], last ? c_halo_next : cs_[rr * T]);
+            }
+          }
+          __syncthreads();                      // everybody is done with this buffer
+        }
+        if (len == m) fwd_row(m - 1, (size_t)(m - 1) * T + tid, x_halo_next, c_halo_next);
       }
       bG = -pi;
     }
+    fence_proxy_async();                      // A, G, R rows go back through the bulk-copy path in the back-substitution
     exA[tid] = bA; exG[tid] = bG; exR[tid] = bR;
     __syncthreads();
     if (active) {
@@ -475,22 +544,42 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream_kernel(const KA
         aif = S.KD * bif;
       }
     }
-    if (active) {
+    {
+      // back-substitution, rows m-2 .. 0 of (R, A, G) staged through shared memory in batches of STG_R rows (descending)
       const double beta = blk ? bif : aif;
-      const double sj = red0[tid] + red1[tid] * beta;
-      const double sp = (jc > 0) ? (red0[tid - 1] + red1[tid - 1] * beta) : 0.0;
-      double cn = sj;
-      size_t a = saddr(T, tid, len - 1);
-      C[a] = cn;
-#pragma unroll 2
-      for (int k = len - 2; k >= 0; --k) {
-        a -= T;
-        if (k >= SPF) {
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(C + a - (size_t)SPF * T));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(FA + a - (size_t)SPF * T));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(FG + a - (size_t)SPF * T));
+      double sp = 0.0, cn = 0.0;
+      if (active) {
+        cn = red0[tid] + red1[tid] * beta;
+        sp = (jc > 0) ? (red0[tid - 1] + red1[tid - 1] * beta) : 0.0;
+        C[saddr(T, tid, len - 1)] = cn;
+      }
+      const int nrows = m - 1, nbatch = (nrows + STG_R - 1) / STG_R;
+      auto issue = [&](const int b) {
+        const int hi = m - 2 - b * STG_R, lo = max(hi - STG_R + 1, 0), nr = hi - lo + 1, buf = b % STG_NBB;
+        const unsigned bytes = (unsigned)nr * T * 8u;
+        double *dst = stg + (size_t)buf * (3 * STG_R * T);
+        mbar_expect_tx(&fullb[buf], 3u * bytes);
+        bulk_g2s(dst, C + (size_t)lo * T, bytes, &fullb[buf]);
+        bulk_g2s(dst + STG_R * T, FA + (size_t)lo * T, bytes, &fullb[buf]);
+        bulk_g2s(dst + 2 * STG_R * T, FG + (size_t)lo * T, bytes, &fullb[buf]);
+      };
+      if (tid == 0) for (int b = 0; b < STG_NBB - 1 && b < nbatch; ++b) issue(b);
+      for (int b = 0; b < nbatch; ++b) {
+        const int buf = b % STG_NBB;
+        if (tid == 0 && b + STG_NBB - 1 < nbatch) issue(b + STG_NBB - 1);
+        mbar_wait(&fullb[buf], (stg_par >> buf) & 1u);
+        stg_par ^= 1u << buf;
+        const int hi = m - 2 - b * STG_R, lo = max(hi - STG_R + 1, 0);
+        const double *rs_ = stg + (size_t)buf * (3 * STG_R * T) + tid, *as_ = rs_ + STG_R * T, *gs_ = as_ + STG_R * T;
+#pragma unroll 1
+        for (int k = hi; k >= lo; --k) {
+          if (k <= len - 2) {
+            const int o = (k - lo) * T;
+            cn = rs_[o] - as_[o] * sp - gs_[o] * cn;
+            C[(size_t)k * T + tid] = cn;
+          }
         }
-        cn = C[a] - FA[a] * sp - FG[a] * cn; C[a] = cn;
+        __syncthreads();
       }
     }
     if (tid == 0) { C[paddr(T, L, 0, n1 - 1)] = aif; C[paddr(T, L, 1, n2 - 1)] = bif; }
