@@ -299,6 +299,22 @@ def test_streaming_interleaved_kernel(oracle, cuda_lib, kind):
     compare(eo, eg)
 
 
+def test_streaming_kernel_row_batches(oracle, cuda_lib):
+    """streaming kernel with columns of ~40 rows: the forward sweep and the back-substitution stage their rows through
+    shared memory in batches of 7 (cp.async.bulk + mbarrier), so this run takes several batches per pass and re-uses
+    every staging buffer and barrier phase; node counts change on the way (growth and resorption)"""
+    pars = []
+    for V, res in ((1e-7, [4000, 6000]), (-1e-7, [4100, 5000]), (2e-7, [5000, 5001])):
+        p = d.pars_MB_growth()
+        p.update(V_ip=V, res=res, MRefin=1.0, Ri=[0.45, 1.0], t_tot=2e4, KD_ar=(0.1, 0.1), Cl_i=0.5, Cr_i=5.0)
+        pars.append(p)
+    eo, _ = d.build_couple_ensemble(pars, oracle, cap_left=9500, cap_right=9500)
+    eg, _ = d.build_couple_ensemble(pars, cuda_lib, cap_left=9500, cap_right=9500)
+    assert eo.run(oracle, max_steps=40) == 0
+    assert eg.run(cuda_lib, max_steps=40, flags=abi.FLAG_FORCE_STREAMING) == 0
+    compare(eo, eg)
+
+
 def test_D1_material_law(oracle, cuda_lib):
     """examples/D1.jl: Stefan driver with the olivine / melt diffusivities recomputed every step from T and the mean
     olivine composition (MBM_LAW_OLIVINE_MELT_D1).  CUDA `pow`/`exp` and glibc's differ by an ulp in D, which feeds
