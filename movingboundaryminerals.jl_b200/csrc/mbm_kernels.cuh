@@ -516,21 +516,21 @@ __device__ inline void chain_build(Scal &Sh, const KArgs &A, const MemberPtrs &P
 __device__ __noinline__ double pchip_slope(const double *x, const double *y, int n, int i) {
   if (i == 0) {
     const double h1 = x[1] - x[0], h2 = x[2] - x[1];
-    const double m1 = (y[1] - y[0]) * (1.0 / h1), m2 = (y[2] - y[1]) * (1.0 / h2);
-    double d = fma(fma(2.0, h1, h2), m1, -(h1 * m2)) * (1.0 / (h1 + h2));
+    const double m1 = (y[1] - y[0]) * frcp_(h1), m2 = (y[2] - y[1]) * frcp_(h2);
+    double d = fma(fma(2.0, h1, h2), m1, -(h1 * m2)) * frcp_(h1 + h2);
     if (m1 * m2 < 0.0 || m1 == 0.0 || m2 == 0.0) d = 0.0;
     return d;
   } else if (i == n - 1) {
     const double h1 = x[n - 1] - x[n - 2], h2 = x[n - 2] - x[n - 3];
-    const double m1 = (y[n - 1] - y[n - 2]) * (1.0 / h1), m2 = (y[n - 2] - y[n - 3]) * (1.0 / h2);
-    double d = fma(fma(2.0, h1, h2), m1, -(h1 * m2)) * (1.0 / (h1 + h2));
+    const double m1 = (y[n - 1] - y[n - 2]) * frcp_(h1), m2 = (y[n - 2] - y[n - 3]) * frcp_(h2);
+    double d = fma(fma(2.0, h1, h2), m1, -(h1 * m2)) * frcp_(h1 + h2);
     if (m1 * m2 < 0.0 || m1 == 0.0 || m2 == 0.0) d = 0.0;
     return d;
   }
-  const double ihm = 1.0 / (x[i] - x[i - 1]), ihp = 1.0 / (x[i + 1] - x[i]);
+  const double ihm = frcp_(x[i] - x[i - 1]), ihp = frcp_(x[i + 1] - x[i]);
   const double mm = (y[i] - y[i - 1]) * ihm, mp = (y[i + 1] - y[i]) * ihp;
   const double wm = 2.0 * ihm, wp = 2.0 * ihp;
-  double d = (wm * mm + wp * mp) * (1.0 / (wm + wp));
+  double d = (wm * mm + wp * mp) * frcp_(wm + wp);
   if (mm * mp < 0.0 || mm == 0.0 || mp == 0.0) d = 0.0;
   const double lim = 3.0 * fmin(fabs(mm), fabs(mp));
   const double ad = fmin(fabs(d), lim);
@@ -550,7 +550,7 @@ __device__ __forceinline__ double pchip_eval_one(const double *x, const double *
   *kout = k; *branch = 3;
   const double x1 = x[k], x2 = x[k + 1], y1 = y[k], y2 = y[k + 1], d1 = d[k], d2 = d[k + 1];
   const double s = Xj - x1, h = x2 - x1;
-  const double ih = 1.0 / h, ih2 = ih * ih, ih3 = ih2 * ih;
+  const double ih = frcp_(h), ih2 = ih * ih, ih3 = ih2 * ih;
   const double s2 = s * s, s3 = s2 * s, h3 = h * h * h, smh = s - h;
   const double t1 = (3.0 * h * s2 - 2.0 * s3) * ih3 * y2;
   const double t2 = (h3 - 3.0 * h * s2 + 2.0 * s3) * ih3 * y1;
@@ -561,13 +561,6 @@ __device__ __forceinline__ double pchip_eval_one(const double *x, const double *
 
 
 // ---- value-code variants used by the tuned kernel (fast reciprocal, walking interval search) -----------
-__device__ __forceinline__ double frcp_(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  // seed error e ~ 2^-20: r (1 + e + e^2) leaves e^3 ~ 2^-60, one dependent FMA less than two Newton steps
-  const double e = fma(-x, r, 1.0);
-  return fma(fma(e, e, e), r, r);
-}
 __device__ __forceinline__ double slope_interior(double ihm, double ihp, double mm, double mp) {
   // d = (w- m- + w+ m+)/(w- + w+), w = 2/h (the factor 2 cancels); zero on sign change / zero secant; limiter 3*min|m|
   const double d = (ihm * mm + ihp * mp) * frcp_(ihm + ihp);
@@ -1012,7 +1005,7 @@ __global__ void __launch_bounds__(T, (T <= 64) ? 512 / T : 1) mbm_step_kernel(co
     }
 
     const int n1 = S.n1, n2 = S.n2, gap = S.gap, N = n1 + n2;
-    const double idt = 1.0 / S.dt;
+    const double idt = frcp_(S.dt);
     const int p = n1 - 1;            // global row of the left interface node
     const int q = n1;                // global row of the right interface node (couples only)
     // -------- partition rows into chunks: block L = rows 0..nbL-1 (left->interface), block R = rows N-1..q+1
@@ -1091,10 +1084,10 @@ __global__ void __launch_bounds__(T, (T <= 64) ? 512 / T : 1) mbm_step_kernel(co
         if (ell == f) subF = subrow;
         // backward elimination over interior rows (ell <= l-1)
         if (ell == l - 1) {
-          const double inv = 1.0 / diag;
+          const double inv = frcp_(diag);
           bA = subrow * inv; bG = sup * inv; bR = rhs * inv;
         } else if (ell < l - 1) {
-          const double inv = 1.0 / (diag - sup * bA);
+          const double inv = frcp_(diag - sup * bA);
           bA = subrow * inv;
           bG = -sup * bG * inv;
           bR = (rhs - sup * bR) * inv;
@@ -1126,7 +1119,7 @@ __global__ void __launch_bounds__(T, (T <= 64) ? 512 / T : 1) mbm_step_kernel(co
         double subrow = sub;
         if (ell == 0 && dir0) { sup = 0.0; subrow = 0.0; }
         if (dirLast && ell == nb - 1) { sup = 0.0; subrow = 0.0; }
-        const double inv = 1.0 / (diag - subrow * Gp);
+        const double inv = frcp_(diag - subrow * Gp);
         const double An = -subrow * Ap * inv + ((ell == f) ? subrow * inv : 0.0);
         const double Gn = sup * inv;
         const double Rn = (rhs - subrow * Rp) * inv;
@@ -1172,12 +1165,13 @@ __global__ void __launch_bounds__(T, (T <= 64) ? 512 / T : 1) mbm_step_kernel(co
     if (!simple) {
       if (bc == BC_FLUX) {
         const double dxl = X[SIDX(p)] - X[SIDX(p - 1)], dxr = X[SIDX(q + 1)] - X[SIDX(q)];
-        const double al = -S.rho1 * S.D_l * (1.0 / dxl), be = S.V * S.rho1 + S.rho1 * S.D_l * (1.0 / dxl);
-        const double ga = -S.V * S.rho2 + S.rho2 * S.D_r * (1.0 / dxr), de = -S.rho2 * S.D_r * (1.0 / dxr);
+        const double idxl = frcp_(dxl), idxr = frcp_(dxr);
+        const double al = -S.rho1 * S.D_l * idxl, be = S.V * S.rho1 + S.rho1 * S.D_l * idxl;
+        const double ga = -S.V * S.rho2 + S.rho2 * S.D_r * idxr, de = -S.rho2 * S.D_r * idxr;
         const double U0 = red0[KL - 1], U1 = red1[KL - 1], W0 = red0[KL + KR - 1], W1 = red1[KL + KR - 1];
         const double ca = be + al * U1, cb = ga + de * W1;
         const double r = -(al * U0 + de * W0);
-        bif = r / (ca * S.KD + cb);
+        bif = r * frcp_(ca * S.KD + cb);
         aif = S.KD * bif;
       } else if (bc == BC_MB) {
         double v[4] = {0.0, 0.0, 0.0, 0.0};
@@ -1191,7 +1185,7 @@ __global__ void __launch_bounds__(T, (T <= 64) ? 512 / T : 1) mbm_step_kernel(co
         const double Vp_ = pow_ndim(X[SIDX(p)], ndim), Vq_ = pow_ndim(X[SIDX(q)], ndim);
         const double wp = 0.5 * (Vq_ - Vp_) + 0.5 * (Vp_ - pow_ndim(X[SIDX(p - 1)], ndim));
         const double wq = 0.5 * (pow_ndim(X[SIDX(q + 1)], ndim) - Vq_) + 0.5 * (Vq_ - Vp_);
-        bif = (S.Mass0 - (v[0] + v[2])) / ((v[1] + wp) * S.KD + (v[3] + wq));
+        bif = (S.Mass0 - (v[0] + v[2])) * frcp_((v[1] + wp) * S.KD + (v[3] + wq));
         aif = S.KD * bif;
       } else {
         aif = a_old; bif = b_old;
