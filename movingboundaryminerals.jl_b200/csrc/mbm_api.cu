@@ -149,6 +149,7 @@ int threads_for(int capS) {
 template <int T>
 int launch_T(const mbm::KArgs &A, int member0, int count, bool use_global, size_t smem_bytes, cudaStream_t s) {
   auto kern = mbm::mbm_step_kernel<T>;
+  if (T <= 64 && !use_global && A.inner_bc == mbm::BC_STEFAN && !getenv("MBM_NO_SPEC")) kern = mbm::mbm_step_kernel<T, (T <= 64) ? mbm::BC_STEFAN : 0>;
   if (!use_global) {
     if (int rc = launch_rc("general kernel: shared-memory opt-in", cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes))) return rc;
   }

@@ -276,8 +276,8 @@ __device__ inline double canonical_total_serial(const double *v, int n) {
 }
 
 // ---- scalar phase of one step (thread 0): dt, time, parameters, interface advection, new node counts ---
-__device__ inline void step_scalars(Scal &S, const KArgs &A, const MemberPtrs &P, int mem, double *X, double *C) {
-  const int bc = A.inner_bc;
+__device__ inline void step_scalars(Scal &S, const KArgs &A, const MemberPtrs &P, int mem, double *X, double *C,
+                                    const int bc) {
   int rc = 0;
   if (bc == BC_NONE) {
     S.dt = xmul(xmul(S.CFL, xmul(S.sdx, S.sdx)), xinv(S.D_l));            // calculate_dt, functions.jl:166
@@ -800,7 +800,11 @@ __device__ __forceinline__ void reduced_apply(const double *fac, double *r0) {
 // ======================================================================================================
 // The kernel
 // ======================================================================================================
-template <int T>
+// SPEC = BC_STEFAN: the instantiation for small Stefan members in shared memory (config 2's sweep): the interface kind
+// and the memory space are compile-time, so the other kinds' branches, the run-ahead chain and the generic-pointer
+// loads drop out of the instruction stream (these members are one warp each, sixteen per SM, every warp at its own
+// place in the code: the full kernel's 250 KB of instructions do not stay in the instruction caches).
+template <int T, int SPEC = 0>
 // small members (one or two warps each) are latency-bound serial code: size the registers for 16 resident warps per SM
 __global__ void __launch_bounds__(T, (T <= 64) ? 512 / T : 1) mbm_step_kernel(const KArgs A, const int member0) {
   extern __shared__ double smem[];
@@ -813,11 +817,11 @@ __global__ void __launch_bounds__(T, (T <= 64) ? 512 / T : 1) mbm_step_kernel(co
   if (mem >= A.M) return;
   const int capS = A.capS;
   const size_t per_cta = 5 * (size_t)capS + (size_t)(capS / 256 + 8);
-  double *base = A.use_global ? (A.workspace + (size_t)blockIdx.x * per_cta) : smem;
+  double *base = (SPEC || !A.use_global) ? smem : (A.workspace + (size_t)blockIdx.x * per_cta);
   double *gtot = base + 5 * (size_t)capS;                          // scan group totals
   double *X = base, *C = base + capS, *Dd = base + 2 * (size_t)capS, *Xn = base + 3 * (size_t)capS,
          *Cn = base + 4 * (size_t)capS;
-  const int bc = A.inner_bc;
+  const int bc = SPEC ? SPEC : A.inner_bc;
   const bool simple = (bc == BC_NONE);
   MemberPtrs P;
   P.t_ar = A.t_ar + (size_t)mem * A.t_stride;
@@ -920,11 +924,12 @@ __global__ void __launch_bounds__(T, (T <= 64) ? 512 / T : 1) mbm_step_kernel(co
   cta_sync<T>();
 
   double *recs = A.recs ? (A.recs + (size_t)blockIdx.x * T * REC_N) : nullptr;
+  const bool chain_kind = (bc == BC_FLUX || bc == BC_MB);     // compile-time false in the Stefan instantiation
   if (tid == 0) {
-    S.use_chain = (recs != nullptr) && (bc == BC_FLUX || bc == BC_MB) && (S.V != 0.0) && (S.MRefin > 1.0) &&
+    S.use_chain = (recs != nullptr) && chain_kind && (S.V != 0.0) && (S.MRefin > 1.0) &&
                   (S.status == 0);
     S.rec_status = 0;
-    if (S.use_chain) {
+    if (chain_kind && S.use_chain) {
       Chain &c = S.ch;
       const int n1 = S.n1;
       c.t = S.t; c.dt = S.dt; c.it = S.it; c.steps = S.steps; c.Ri1 = S.Ri1; c.dx1 = S.dx1; c.dx2 = S.dx2;
@@ -941,7 +946,7 @@ __global__ void __launch_bounds__(T, (T <= 64) ? 512 / T : 1) mbm_step_kernel(co
   // ======================================= time loop ===================================================
   int lpos = 0, lcount = 0;   // every thread tracks the batch cursor itself (no shared-memory race)
   while (true) {
-    if (S.use_chain) {
+    if (chain_kind && S.use_chain) {
       // ---------- run-ahead: refill the batch of step records when it is exhausted ----------
       if (lpos >= lcount) {
         if (S.ch.done) break;
@@ -999,7 +1004,7 @@ __global__ void __launch_bounds__(T, (T <= 64) ? 512 / T : 1) mbm_step_kernel(co
     } else {
       if (S.status != 0 || !(S.t < S.t_tot) || (A.max_steps > 0 && S.steps >= A.max_steps)) break;
       cta_sync<T>();   // everyone has read the loop condition before thread 0 changes S
-      if (tid == 0) step_scalars(S, A, P, mem, X, C);
+      if (tid == 0) step_scalars(S, A, P, mem, X, C, bc);
       cta_sync<T>();
       if (S.status != 0) break;
     }
@@ -1236,7 +1241,7 @@ __global__ void __launch_bounds__(T, (T <= 64) ? 512 / T : 1) mbm_step_kernel(co
         for (int i = tid; i < nl; i += T) XLn[i + 1] = xmul(xmul(XLn[i + 1], Ri1), isum);
         if (tid == 0) XLn[0] = xmul(xmul(0.0, Ri1), isum);
         cta_sync<T>();
-        if (S.use_chain) {
+        if (chain_kind && S.use_chain) {
           if (tid == 0 && S.rec_status) S.status = S.rec_status;
         } else if (tid == 0) {                                              // :406-408
           const double Sg = xsub(Ri2, Ri1);
