@@ -133,7 +133,77 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
   HistCache hc;
   if (tid == 0) hist_load(hc, P, S.hidx);
 
+  // ---- scalar batches (constant diffusivities): with V_ip == 0 and no Arrhenius law the per-step scalars do not depend
+  // on the solution and dt only changes on the clipped last step, so thread 0 runs the time chain (t += dt, exact adds)
+  // for SB steps ahead and the lanes of warp 0 interpolate KD(t), T(t) of one step each (same arithmetic and cursor
+  // semantics as update_t_dependent_param!, functions.jl:1350-1378).  A step then reads its record; there is no scalar
+  // phase of thread 0 and no barrier pair around it.  Arrhenius members keep the per-step scalar phase (D feeds dt).
+  // The records live in the unused tail of the block-sum scratch S.red (block_sum4 touches its first 4 * T / 32 <= 32
+  // doubles): a kilobyte more static shared memory per CTA costs the fourth resident CTA at config 3's size.
+  constexpr int SB = 16;
+  double *const srec = S.red + 32;            // dt, t, KD, T of the batch (SB * 4 doubles)
+  int *const srst = reinterpret_cast<int *>(S.red + 32 + SB * 4);   // status per record (SB ints)
+  int &srcount = S.Fl;                        // records in the batch (S.Fl is not used by this kernel otherwise)
+  static_assert(32 + SB * 4 + SB / 2 <= 128, "records must fit S.red");
+  const bool batched = !S.arrhenius;
+  int rpos = 0, rcount = 0;
+  double fact_dt = 0.0;                       // dt of the resident factorisation (batched mode; 0 = none yet)
+
   while (true) {
+    bool refactor;
+    double dt_k, KD_k;
+    if (batched) {
+      if (S.status != 0) break;
+      if (rpos == rcount) {
+        __syncthreads();
+        if (tid == 0) {
+          if (!(S.D_l == dtD_l && S.D_r == dtD_r)) {
+            const double mn = fmin(S.dx1, S.dx2), mxD = fmax(S.D_l, S.D_r);
+            dt_full = xmul(xmul(xmul(xmul(mn, mn), xinv(mxD)), 50.0), S.CFL);
+            dtD_l = S.D_l; dtD_r = S.D_r;
+          }
+          int cnt = 0;
+          double t = S.t;
+          long long steps = S.steps;
+          while (cnt < SB && t < S.t_tot && !(A.max_steps > 0 && steps >= A.max_steps)) {
+            double dt = dt_full;
+            t = xadd(t, dt);
+            if (t > S.t_tot) { dt = xsub(dt, xsub(t, S.t_tot)); t = S.t_tot; }
+            srec[4 * cnt] = dt; srec[4 * cnt + 1] = t;
+            ++cnt; ++steps;
+          }
+          srcount = cnt;
+        }
+        __syncthreads();
+        rcount = srcount; rpos = 0;
+        if (tid < 32) {                         // warp 0: one step per lane
+          int hi_new = 0;
+          if (tid < rcount) {
+            HistCache h;
+            hist_load(h, P, S.hidx);
+            double KD, Tt, Dl, Dr;
+            const int rc = chain_update_params(S, A, P, srec[4 * tid + 1], h, &KD, &Tt, &Dl, &Dr);
+            srec[4 * tid + 2] = KD; srec[4 * tid + 3] = Tt; srst[tid] = rc;
+            hi_new = h.i;
+          }
+          __syncwarp();
+          if (rcount > 0 && tid == rcount - 1) S.hidx = hi_new;      // cursor of the batch's last step
+        }
+        __syncthreads();
+        if (rcount == 0) break;
+      }
+      dt_k = srec[4 * rpos]; KD_k = srec[4 * rpos + 2];
+      const int st_k = srst[rpos];
+      if (tid == 0) {
+        S.dt = dt_k; S.t = srec[4 * rpos + 1]; S.it += 1;
+        if (st_k) S.status = st_k;
+        else { S.KD = KD_k; S.T = srec[4 * rpos + 3]; S.node_steps += N; }
+      }
+      rpos += 1;
+      if (st_k) break;
+      refactor = (dt_k != fact_dt);
+      fact_dt = dt_k;
+    } else {
     if (S.status != 0 || !(S.t < S.t_tot) || (A.max_steps > 0 && S.steps >= A.max_steps)) break;
     __syncthreads();
     if (tid == 0) {
@@ -160,10 +230,12 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
     }
     __syncthreads();
     if (S.status != 0) break;
+    refactor = S.rec_status != 0; dt_k = S.dt; KD_k = S.KD;
+    }
 
-    if (S.rec_status) {
+    if (refactor) {
       // ---------------- coefficient sweep: factorise the step matrix (fill_matrix!, functions.jl:510-549) -------------
-      const double idt = frcp(S.dt);
+      const double idt = frcp(dt_k);
       const double Dph = blk ? S.D_r : S.D_l;
       if (active) {
         double x_self = X[s0], x_prev = 0.0;
@@ -298,8 +370,8 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
     double aif, bif;
     if (bc == BC_FLUX) {
       const double al = S.cu0, de = S.cu1, ca = S.cu2, cb = S.cd0;
-      bif = -(al * red0[red_ix<T>(KL - 1)] + de * red0[red_ix<T>(KL + KR - 1)]) * frcp(ca * S.KD + cb);
-      aif = S.KD * bif;
+      bif = -(al * red0[red_ix<T>(KL - 1)] + de * red0[red_ix<T>(KL + KR - 1)]) * frcp(ca * KD_k + cb);
+      aif = KD_k * bif;
     } else if (mb) {
       double v[4] = {0.0, 0.0, 0.0, 0.0};
       if (active) {
@@ -312,8 +384,8 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
       const double Vp_ = powd<NDIM>(X[p]), Vq_ = powd<NDIM>(X[q]);
       const double wp = 0.5 * (Vq_ - Vp_) + 0.5 * (Vp_ - powd<NDIM>(X[p - 1]));
       const double wq = 0.5 * (powd<NDIM>(X[q - 1]) - Vq_) + 0.5 * (Vq_ - Vp_);
-      bif = (S.Mass0 - (v[0] + v[2])) * frcp((v[1] + wp) * S.KD + (v[3] + wq));
-      aif = S.KD * bif;
+      bif = (S.Mass0 - (v[0] + v[2])) * frcp((v[1] + wp) * KD_k + (v[3] + wq));
+      aif = KD_k * bif;
     } else { aif = a_old; bif = b_old; }
     // ---------------- back-substitution -----------------------------------------------------------------------------------
     if (active) {
