@@ -135,6 +135,26 @@ def test_resume_equals_single_call(cuda_lib):
         assert np.array_equal(ea.arrays[k], eb.arrays[k]), k
 
 
+def test_fixed_interface_resume_and_batches(oracle, cuda_lib):
+    """fixed-interface kernel (V_ip = 0): its scalar batches (16 steps of the time chain ahead) must not show: calls of
+    5 + 9 + 23 steps (batches cut short by max_steps, resumed mid-history) == one call of 37 steps, bit for bit, and
+    both match the oracle; constant diffusivities (B1: batched) and an Arrhenius law (B2: per-step scalar phase)"""
+    for pars, tol in (([d.pars_B1()], 1e-10), ([d.pars_B2()], 2e-9)):       # Arrhenius: CUDA exp vs glibc exp (see compare)
+        ea, _ = d.build_couple_ensemble(pars, cuda_lib)
+        eb = ea.copy()
+        eo, _ = d.build_couple_ensemble(pars, oracle)
+        assert ea.run(cuda_lib, max_steps=37) == 0
+        for n in (5, 9, 23):
+            assert eb.run(cuda_lib, max_steps=n) == 0
+        assert eo.run(oracle, max_steps=37) == 0
+        for k in ("x_left", "C_left", "x_right", "C_right", "res", "it", "Ri", "t", "dt"):
+            assert np.array_equal(ea.arrays[k], eb.arrays[k]), k
+        assert np.all(ea.status == 0) and np.all(eo.status == 0)
+        assert np.array_equal(ea.it, eo.it) and np.array_equal(ea.res, eo.res)
+        for a, b in zip(eo.member(0), ea.member(0)):
+            assert np.max(np.abs(a - b)) <= tol * np.max(np.abs(a))
+
+
 @pytest.mark.parametrize("threads", ["32", "64", "128", "256"])
 def test_thread_configs(oracle, cuda_lib, threads, monkeypatch):
     """every CTA width gives the same integers and 1e-10 profiles (different chunking of the solve)"""
