@@ -33,7 +33,7 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
-TRAFFIC_BYTES_8192 = 485.8e6 + 590.6e6     # ncu, see roofline.traffic below
+TRAFFIC_BYTES_8192 = 486.3e6 + 596.0e6     # ncu (profiles/r01_ncu_v2kernel_head_summary.txt), see roofline.traffic below
 sys.path.insert(0, str(ROOT))
 
 
@@ -308,7 +308,7 @@ def main():
                 "traffic": TRAFFIC_BYTES_8192 * args.members_per_gpu / 8192.0,
                 "peak_source": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "flops_per_node_step": flops_per_ns, "kernel": "mbm_step_kernel_v2<256,2>", "kernel_ms_per_launch": kernel_ms,
-                "traffic_note": "bytes per launch from ncu (486 MB read + 591 MB written at 8192 members): the state and the histories cross HBM once per launch, not once per step (0.16 % of DRAM throughput); algorithmic streaming traffic would be 32 B x node-steps = 157 GB per launch",
+                "traffic_note": "bytes per launch from ncu (486 MB read + 596 MB written at 8192 members, profiles/r01_ncu_v2kernel_head_summary.txt): the state and the histories cross HBM once per launch, not once per step (0.16 % of DRAM throughput); algorithmic streaming traffic would be 32 B x node-steps = 157 GB per launch",
                 "hbm_view": {"bound": "hbm", "achieved": per_gpu * 32 * 1e-9, "peak": hbm, "unit": "GB/s",
                              "frac": per_gpu * 32 * 1e-9 / hbm, "bytes_per_node_step": 32,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
