@@ -61,11 +61,13 @@ __device__ __forceinline__ double pow_ndim(double x, int ndim) {
 }
 
 // LinRange(a,b,len)[i], 0-based (Base.lerpi)
-__device__ __noinline__ double linrange_at(double a, double b, long long len, long long i) {
-  long long d = (len - 1 > 1) ? (len - 1) : 1;
-  double t = xdiv((double)i, (double)d);
+// (node counts are 32-bit: the int -> double conversions are single instructions and exact)
+__device__ __forceinline__ double linrange_at_inl(double a, double b, int len, int i) {
+  const int d = (len - 1 > 1) ? (len - 1) : 1;
+  const double t = xdiv((double)i, (double)d);
   return xadd(xmul(xsub(1.0, t), a), xmul(t, b));
 }
+__device__ __noinline__ double linrange_at(double a, double b, int len, int i) { return linrange_at_inl(a, b, len, i); }
 
 // x^n and x^(n-1) in one pass: the two pow_body calls of a Newton iteration square the same x, so the (x, xnlo)
 // sequence is computed once and only the two y accumulations differ.  Every operation of either call is executed

@@ -126,7 +126,7 @@ __device__ __forceinline__ void pchip_run_stream(const double *X, const double *
   const int tid = threadIdx.x;
   const bool MIR = (phase != 0);                      // runtime: both phases run one instruction stream
   const double sg = MIR ? -1.0 : 1.0;
-  auto newx = [&](int pi) { return linrange_at(lr_a, lr_b, nn, MIR ? (nn - 1 - pi) : pi); };     // reference node order
+  auto newx = [&](int pi) { return linrange_at_inl(lr_a, lr_b, nn, MIR ? (nn - 1 - pi) : pi); };     // reference node order
   auto emit = [&](int k, double xj, double val, int kk, int br) {
     const size_t an = saddr(T, tid, k);
     Xn[an] = xj; Cn[an] = val;
