@@ -36,9 +36,16 @@ constexpr int SPF = MBM_SPF;   // software prefetch distance of the regrid walk,
 #ifndef MBM_STG_R
 #define MBM_STG_R 7
 #endif
-constexpr int STG_R = MBM_STG_R, STG_NBF = 3, STG_NBB = 2;
-constexpr int STG_BYTES = STG_R * STG_NBF * 2 * 256 * 8;            // = STG_R * STG_NBB * 3 * 256 * 8 = 86016
-static_assert(STG_R * STG_NBB * 3 * 256 * 8 == STG_BYTES, "forward and backward staging share one allocation");
+#ifndef MBM_STG_NBF
+#define MBM_STG_NBF 3
+#endif
+#ifndef MBM_STG_NBB
+#define MBM_STG_NBB 2
+#endif
+constexpr int STG_R = MBM_STG_R, STG_NBF = MBM_STG_NBF, STG_NBB = MBM_STG_NBB;
+constexpr int STG_BYTES_F = STG_R * STG_NBF * 2 * 256 * 8, STG_BYTES_B = STG_R * STG_NBB * 3 * 256 * 8;
+constexpr int STG_BYTES = STG_BYTES_F > STG_BYTES_B ? STG_BYTES_F : STG_BYTES_B;   // one allocation for both passes (86016 by default)
+static_assert(STG_NBF <= 8 && STG_NBB <= STG_NBF, "staging barriers: fullb[STG_NBF]");
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
