@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -19,8 +20,9 @@ thread_local cudaStream_t g_user_stream = nullptr;
 thread_local bool g_have_user_stream = false;
 thread_local double g_last_kernel_seconds = 0.0;
 thread_local long long g_last_kernel_launches = 0;
-double g_last_kernel_seconds_any = 0.0;
-long long g_last_kernel_launches_any = 0;
+// last-call metrics readable from any host thread (bench / smoke): atomics, written once per call
+std::atomic<double> g_last_kernel_seconds_any{0.0};
+std::atomic<long long> g_last_kernel_launches_any{0};
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -38,6 +40,16 @@ int launch_rc(const char *what, cudaError_t e) {
   fprintf(stderr, "[mbm_b200] %s failed: %s (%s)\n", what, cudaGetErrorName(e), cudaGetErrorString(e));
   return MBM_RC_CUDA;
 }
+
+// make `device` current for the lifetime of the object, then restore the caller's device
+struct DeviceScope {
+  int prev = -1, rc = 0;
+  explicit DeviceScope(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (cudaSetDevice(device) != cudaSuccess) rc = MBM_RC_CUDA;
+  }
+  ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 // staging of one shard: device copies of host arrays, copied back on request
 // Host-buffer calls are cut into pieces that run on their own streams (one host thread each).  Left alone, all pieces
@@ -109,7 +121,8 @@ struct Stage {
     cudaError_t e = cudaMallocAsync(&d, count * sizeof(Tp), stream);
     if (e != cudaSuccess) { rc = (e == cudaErrorMemoryAllocation) ? MBM_RC_OOM : MBM_RC_CUDA; return nullptr; }
     owned.push_back(d);
-    cudaMemsetAsync(d, 0, count * sizeof(Tp), stream);
+    e = cudaMemsetAsync(d, 0, count * sizeof(Tp), stream);
+    if (e != cudaSuccess) { rc = MBM_RC_CUDA; fprintf(stderr, "[mbm_b200] device memset failed: %s\n", cudaGetErrorString(e)); return nullptr; }
     items.push_back({(void *)h, d, count * sizeof(Tp), true});
     return (Tp *)d;
   }
@@ -338,7 +351,12 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
   }
   A.use_global = use_global ? 1 : 0;
   const bool couple_pv = (A.inner_bc == MBM_BC_FLUX || A.inner_bc == MBM_BC_MB);
-  bool use_v2 = couple_pv && !use_global && !getenv("MBM_NO_CHAIN") && !getenv("MBM_NO_V2") && A.ndim >= 1 && A.ndim <= 3;
+  // MBM_FLAG_NEWTON_WARM: the run-ahead chain (tuned kernel, and the general kernel's batched Newton) always solves the
+  // cold-start problems of the reference (functions.jl:734), so warm-start calls take the general kernel's serial path,
+  // the one that starts newton_solver from the member's previous root like the oracle does (mbm_oracle.c, regrid)
+  const bool newton_warm = (flags & MBM_FLAG_NEWTON_WARM) != 0;
+  const bool no_chain = newton_warm || getenv("MBM_NO_CHAIN");
+  bool use_v2 = couple_pv && !use_global && !no_chain && !getenv("MBM_NO_V2") && A.ndim >= 1 && A.ndim <= 3;
   int T2 = 256;
   if (use_v2) {
     int smem_sm = 0;
@@ -346,7 +364,7 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
     v2_plan(A.capL, A.capR, A.pad3_, smem_sm, A.ndim, &T2, &A.kcapL);
     if (A.kcapL < 8) use_v2 = false;
   }
-  if (couple_pv && !getenv("MBM_NO_CHAIN")) {
+  if (couple_pv && !no_chain) {
     const int Tr = (use_v2 && T2 > T) ? T2 : T;
     A.recs = (double *)st->scratch((size_t)chunk * (size_t)Tr * mbm::REC_N * sizeof(double));
     if (!A.recs) return st->rc ? st->rc : MBM_RC_OOM;
@@ -368,7 +386,11 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
     CK(cudaMemsetAsync(A.steps_done, 0, (size_t)count * sizeof(long long), s));
   }
   const bool async = g_have_user_stream && st->device_ptrs;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  struct EventPair {                             // destroyed on every exit path of this function
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~EventPair() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+  } ev;
+  cudaEvent_t &e0 = ev.e0, &e1 = ev.e1;
   if (!async) {
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -435,8 +457,6 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
   CK(cudaStreamSynchronize(s));
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   if (kernel_seconds) *kernel_seconds = ms * 1e-3;
   return 0;
 }
@@ -444,21 +464,27 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
 // keep the stream-ordered allocator's memory cached between calls (default: released at the next synchronisation,
 // which re-maps hundreds of MB of scratch on every call)
 void keep_pool_cached(int device) {
-  static bool done[64] = {false};
-  if (device < 0 || device >= 64 || done[device]) return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    unsigned long long thr = ~0ull;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
-  done[device] = true;
+  static std::once_flag once[64];                // shard threads of concurrent calls race here: once per device
+  if (device < 0 || device >= 64) return;
+  std::call_once(once[device], [device] {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  });
 }
 
+// argument checks first (no CUDA call), the device check last: a bad argument is reported as such on any machine, and
+// a well-formed call on a machine without a GPU fails loudly with MBM_RC_NO_DEVICE (there is no CPU path)
 int check_common(const mbm_common *c) {
   if (!c || c->abi_version != MBM_ABI_VERSION) return MBM_RC_BAD_ARG;
   if (c->n_members < 0 || c->cap_left < 3 || c->hist_len < 2) return MBM_RC_BAD_ARG;
   if (c->n_devices < 1) return MBM_RC_BAD_ARG;
   if ((c->flags & MBM_FLAG_DEVICE_POINTERS) && c->n_devices != 1) return MBM_RC_BAD_ARG;
+  return 0;
+}
+int check_devices(const mbm_common *c) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return MBM_RC_NO_DEVICE;
   for (int i = 0; i < c->n_devices; ++i) {
@@ -769,6 +795,20 @@ int mbm_couple_batch(const mbm_common *c, const mbm_couple_params *p, mbm_couple
       !io->it || !io->status)
     return MBM_RC_BAD_ARG;
   if (c->flags & (MBM_FLAG_SOLVER_FAITHFUL | MBM_FLAG_SUM_JULIA)) return MBM_RC_UNSUPPORTED;  // oracle-only modes
+  // every pointer a kernel would dereference for this interface kind is checked here, before any launch: a NULL that
+  // reaches a kernel is an illegal-address fault and a sticky context error for the whole process
+  if (c->dt_mode < MBM_DT_FIND_DT || c->dt_mode > MBM_DT_SIMPLE) return MBM_RC_BAD_ARG;
+  if (c->inner_bc == MBM_BC_STEFAN) {
+    if (c->dt_mode != MBM_DT_STEFAN) return MBM_RC_BAD_ARG;
+    if (!p->coeff_up || !p->coeff_do || !p->C_leftB || !p->C_rightB) return MBM_RC_BAD_ARG;
+  } else {
+    if (c->dt_mode == MBM_DT_STEFAN || c->dt_mode == MBM_DT_SIMPLE) return MBM_RC_BAD_ARG;
+  }
+  if (p->nd < 0) return MBM_RC_BAD_ARG;
+  if (p->nd > 0 && (p->nd < 2 || !p->dens_X || !p->dens_T || !p->dens_left || !p->dens_right)) return MBM_RC_BAD_ARG;
+  if (p->law != MBM_LAW_NONE && p->law != MBM_LAW_OLIVINE_MELT_D1) return MBM_RC_BAD_ARG;
+  if (p->law != MBM_LAW_NONE && (!p->law_par || c->inner_bc != MBM_BC_STEFAN)) return MBM_RC_BAD_ARG;
+  if ((rc = check_devices(c))) return rc;
   return run_sharded(c, [&](int m0, int m1, int dev, double *ks) { return couple_shard(c, p, io, m0, m1, dev, ks); });
 }
 
@@ -793,15 +833,20 @@ int mbm_simple_diff_batch(const mbm_common *c, const mbm_simple_params *p, mbm_s
     return MBM_RC_BAD_ARG;
   if (!io->x || !io->C || !io->res || !io->t || !io->dt || !io->it || !io->status) return MBM_RC_BAD_ARG;
   if (c->flags & (MBM_FLAG_SOLVER_FAITHFUL | MBM_FLAG_SUM_JULIA)) return MBM_RC_UNSUPPORTED;
+  if ((rc = check_devices(c))) return rc;
   return run_sharded(c, [&](int m0, int m1, int dev, double *ks) { return simple_shard(c, p, io, m0, m1, dev, ks); });
 }
 
 int mbm_create_grid(int32_t M, int32_t capL, int32_t capR, const double *Ri, const int64_t *res, const double *MRefin,
                     double *x_left, double *x_right, double *dx1, double *dx2, double *newton_R, int32_t *status) {
+  if (M < 0 || capL < 3 || capR < 3) return MBM_RC_BAD_ARG;
+  if (M > 0 && (!Ri || !res || !MRefin || !x_left || !x_right || !status)) return MBM_RC_BAD_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return MBM_RC_NO_DEVICE;
-  if (M <= 0) return 0;
-  if (!Ri || !res || !MRefin || !x_left || !x_right || !status) return MBM_RC_BAD_ARG;
+  if (M == 0) return 0;
+  // the pre-loop helpers run on device 0 whatever device the calling thread had current, and restore it
+  DeviceScope dev_scope(0);
+  if (dev_scope.rc) return dev_scope.rc;
   Stage st;
   CK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
   const size_t n = (size_t)M;
@@ -828,10 +873,13 @@ int mbm_create_grid(int32_t M, int32_t capL, int32_t capR, const double *Ri, con
 
 int mbm_calc_mass_vol(int32_t M, int32_t ndim, int32_t capL, int32_t capR, const double *x_left, const double *x_right,
                       const double *C_left, const double *C_right, const int64_t *res, const double *rho, double *Mass) {
+  if (M < 0 || capL < 1 || capR < 1 || ndim < 1 || ndim > 3) return MBM_RC_BAD_ARG;
+  if (M > 0 && (!x_left || !x_right || !C_left || !C_right || !res || !rho || !Mass)) return MBM_RC_BAD_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return MBM_RC_NO_DEVICE;
-  if (M <= 0) return 0;
-  if (!x_left || !x_right || !C_left || !C_right || !res || !rho || !Mass) return MBM_RC_BAD_ARG;
+  if (M == 0) return 0;
+  DeviceScope dev_scope(0);
+  if (dev_scope.rc) return dev_scope.rc;
   Stage st;
   CK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
   const size_t n = (size_t)M;

@@ -1396,6 +1396,8 @@ __global__ void __launch_bounds__(T) mbm_create_grid_kernel(int M, int capL, int
   if (tid == 0) st = 0;
   __syncthreads();
   if (nr1 < 3 || nr2 < 3 || nr1 > capL || nr2 > capR) { if (tid == 0) status[mem] = 10; return; }
+  // graded meshes: the canonical scan keeps one group total per 32 tiles of 9 in gtot[1024] (capacity, status 10)
+  if (MR != 1.0 && (nr1 > 1024 * 32 * CSO_TILE || nr2 > 1024 * 32 * CSO_TILE)) { if (tid == 0) status[mem] = 10; return; }
   if (MR == 1.0) {
     for (int i = tid; i < nr1; i += T) XL[i] = linrange_at(0.0, Ri1, nr1, i);
     for (int i = tid; i < nr2; i += T) XR[i] = linrange_at(Ri1, Ri2, nr2, i);

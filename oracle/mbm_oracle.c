@@ -881,6 +881,22 @@ int mbm_couple_batch(const mbm_common *c, const mbm_couple_params *p, mbm_couple
   if (rc) return rc;
   if (!p || !io || c->cap_right < 3) return MBM_RC_BAD_ARG;
   if (c->inner_bc < MBM_BC_FLUX || c->inner_bc > MBM_BC_DIRICHLET_HOLD) return MBM_RC_BAD_ARG;
+  /* the same argument checks as the CUDA library's entry point (error behaviour is part of the ABI) */
+  if (!p->Di || !p->rho || !p->t_tot || !p->CFL || !p->MRefin || !p->BCout || !p->resmin || !p->t_ar || !p->T_ar)
+    return MBM_RC_BAD_ARG;
+  if (c->inner_bc != MBM_BC_STEFAN && !p->KD_ar) return MBM_RC_BAD_ARG;
+  if (!io->x_left || !io->C_left || !io->x_right || !io->C_right || !io->res || !io->Ri || !io->t || !io->dt ||
+      !io->it || !io->status)
+    return MBM_RC_BAD_ARG;
+  if (c->dt_mode < MBM_DT_FIND_DT || c->dt_mode > MBM_DT_SIMPLE) return MBM_RC_BAD_ARG;
+  if (c->inner_bc == MBM_BC_STEFAN) {
+    if (c->dt_mode != MBM_DT_STEFAN) return MBM_RC_BAD_ARG;
+    if (!p->coeff_up || !p->coeff_do || !p->C_leftB || !p->C_rightB) return MBM_RC_BAD_ARG;
+  } else if (c->dt_mode == MBM_DT_STEFAN || c->dt_mode == MBM_DT_SIMPLE) return MBM_RC_BAD_ARG;
+  if (p->nd < 0) return MBM_RC_BAD_ARG;
+  if (p->nd > 0 && (p->nd < 2 || !p->dens_X || !p->dens_T || !p->dens_left || !p->dens_right)) return MBM_RC_BAD_ARG;
+  if (p->law != MBM_LAW_NONE && p->law != MBM_LAW_OLIVINE_MELT_D1) return MBM_RC_BAD_ARG;
+  if (p->law != MBM_LAW_NONE && (!p->law_par || c->inner_bc != MBM_BC_STEFAN)) return MBM_RC_BAD_ARG;
   const int64_t M = c->n_members, capL = c->cap_left, capR = c->cap_right;
 #pragma omp parallel
   {

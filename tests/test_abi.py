@@ -65,3 +65,35 @@ def test_missing_library_is_an_error(monkeypatch, tmp_path):
     with pytest.raises(RuntimeError):
         abi.load_cuda_library()
     monkeypatch.setattr(abi, "_cuda_lib", None)
+
+
+def test_bad_arguments_are_reported_before_the_device_check():
+    """argument checks come first and need no GPU: a malformed call is MBM_RC_BAD_ARG (-1) on any machine; only a
+    well-formed call reaches the device check (MBM_RC_NO_DEVICE here, a launch on a GPU box).  The oracle exports
+    the same ABI and rejects the same calls."""
+    from mbm_b200 import drivers as d
+    from oracle import load
+    cuda = abi.load_cuda_library()
+    ora = load.load()
+    for lib in (cuda, ora):
+        ens, _ = d.build_couple_ensemble([d.pars_DCGMB()], ora)
+        c, p, io = ens.structs(max_steps=1)
+        c.dt_mode = 9
+        assert lib.mbm_couple_batch(C.byref(c), C.byref(p), C.byref(io)) == -1
+        c.dt_mode = abi.DT_STEFAN; c.inner_bc = abi.BC_STEFAN              # Stefan without its coefficient arrays
+        assert lib.mbm_couple_batch(C.byref(c), C.byref(p), C.byref(io)) == -1
+        assert lib.mbm_stefan_xt_batch(C.byref(c), C.byref(p), C.byref(io)) == -1
+        c.dt_mode = abi.DT_FIND_DT; c.inner_bc = abi.BC_MB
+        p.nd = 3                                                           # density table announced, pointers NULL
+        assert lib.mbm_couple_batch(C.byref(c), C.byref(p), C.byref(io)) == -1
+        p.nd = 0; p.law = abi.LAW_OLIVINE_MELT_D1                          # material law without parameters
+        assert lib.mbm_couple_batch(C.byref(c), C.byref(p), C.byref(io)) == -1
+        p.law = 0; c.abi_version = abi.ABI_VERSION + 1
+        assert lib.mbm_couple_batch(C.byref(c), C.byref(p), C.byref(io)) == -1
+        c.abi_version = abi.ABI_VERSION
+        io.x_left = None
+        assert lib.mbm_couple_batch(C.byref(c), C.byref(p), C.byref(io)) == -1
+    if cuda.mbm_device_count() == 0:
+        ens, _ = d.build_couple_ensemble([d.pars_DCGMB()], ora)
+        c, p, io = ens.structs(max_steps=1)
+        assert cuda.mbm_couple_batch(C.byref(c), C.byref(p), C.byref(io)) == -5

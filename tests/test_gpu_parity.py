@@ -394,3 +394,43 @@ def test_checksum_is_optional_and_does_not_change_values(cuda_lib):
     assert np.all(ea.status == 0) and np.all(eb.status == 0)
     for k in ("x_left", "C_left", "x_right", "C_right", "res", "it", "Ri", "t", "Mass", "node_steps"):
         assert np.array_equal(ea.arrays[k], eb.arrays[k]), k
+
+
+def test_newton_warm_flag_matches_oracle(oracle, cuda_lib):
+    """MBM_FLAG_NEWTON_WARM: warm-start calls take the kernel path that starts newton_solver from the member's
+    previous root, as the oracle does (mbm_oracle.c, regrid) - same iterates, so the 1e-10 bar holds with the flag
+    set, and the result differs from the cold-start run (the flag is not silently ignored)."""
+    pars = []
+    for V in (-1e-7, 1e-7):
+        p = d.pars_MB_growth(); p.update(V_ip=V, res=[100, 150]); pars.append(p)
+    p = d.pars_B5(); pars_flux = [p]
+    for plist in (pars, pars_flux):
+        eo, eg = run_both(plist, oracle, cuda_lib, 300, flags=abi.FLAG_NEWTON_WARM)
+        compare(eo, eg)
+        assert _relerr(eo.arrays["newton_R"], eg.arrays["newton_R"]) < 1e-15
+    # the flag is honoured, not ignored: warm and cold start stop at different iterates of the same root
+    ew, _ = d.build_couple_ensemble(pars, cuda_lib)
+    assert ew.run(cuda_lib, max_steps=300, flags=abi.FLAG_MASS_FINAL | abi.FLAG_NEWTON_WARM) == 0
+    ec, _ = d.build_couple_ensemble(pars, cuda_lib)
+    assert ec.run(cuda_lib, max_steps=300, flags=abi.FLAG_MASS_FINAL) == 0
+    assert not np.array_equal(ec.arrays["newton_R"], ew.arrays["newton_R"])
+    assert _relerr(ec.arrays["newton_R"], ew.arrays["newton_R"]) < 1e-8
+
+
+def test_bad_arguments_are_rejected_before_any_launch(cuda_lib):
+    """mbm_couple_batch checks every pointer its interface kind dereferences (a NULL reaching a kernel would be an
+    illegal-address fault and a sticky context error): Stefan coefficients, density tables, law parameters, dt_mode."""
+    import ctypes as C
+    ens, _ = d.build_couple_ensemble([d.pars_DCGMB()], cuda_lib)
+    common, params, io = ens.structs(max_steps=2)
+    assert cuda_lib.mbm_couple_batch(C.byref(common), C.byref(params), C.byref(io)) == 0
+    common.inner_bc = abi.BC_STEFAN; common.dt_mode = abi.DT_STEFAN         # Stefan without coefficient arrays
+    assert cuda_lib.mbm_couple_batch(C.byref(common), C.byref(params), C.byref(io)) == -1
+    common.inner_bc = abi.BC_MB; common.dt_mode = 7
+    assert cuda_lib.mbm_couple_batch(C.byref(common), C.byref(params), C.byref(io)) == -1
+    common.dt_mode = abi.DT_FIND_DT; params.nd = 4                          # density table announced, pointers NULL
+    assert cuda_lib.mbm_couple_batch(C.byref(common), C.byref(params), C.byref(io)) == -1
+    params.nd = 0; params.law = abi.LAW_OLIVINE_MELT_D1                     # law without parameters / outside Stefan
+    assert cuda_lib.mbm_couple_batch(C.byref(common), C.byref(params), C.byref(io)) == -1
+    params.law = 0
+    assert cuda_lib.mbm_couple_batch(C.byref(common), C.byref(params), C.byref(io)) == 0   # the context is still healthy
