@@ -52,8 +52,12 @@ struct KArgs {
 // the mesh quantities it needs are closed-form in two scan totals (csA, csB) that only change when the
 // left node count changes.  Thread 0 runs the chain for up to T steps, then T threads solve the T
 // cold-start Newton problems of reference src/functions.jl:732-757 in parallel (bit-identical iterates).
+// REC_N1S / REC_N2S: node counts of the step's solve (after the node insertion).  REC_PA..REC_PE are filled by the
+// tuned kernel's refill (one thread per record): pairs of 32-bit integers in one slot each, (lo | hi) =
+// (n1s | n2s), (nr1 | nr2), (m | KL), (KR | mq), (KLq | KRq), (status | warn) - the step's node counts and work partitions, so that
+// every thread reads what it needs from the staged record and no thread works the step's scalars out for the others.
 enum { REC_DT = 0, REC_T, REC_KD, REC_TEMP, REC_DL, REC_DR, REC_RI1, REC_D, REC_R, REC_NR1, REC_NR2, REC_STATUS,
-       REC_WARN, REC_IT, REC_N };
+       REC_WARN, REC_IT, REC_N1S, REC_N2S, REC_PA, REC_PB, REC_PC, REC_PD, REC_PE, REC_PF, REC_N };
 struct Chain {
   double t, dt, Ri1, dx1, dx2, D_l, D_r, xl_m2, xr_1, csA, csB;
   long long it, steps;
@@ -70,7 +74,7 @@ struct Scal {
   double lp0, lp1, lp2, lp3, lp4;    // parameters of the in-loop material law (MBM_LAW_OLIVINE_MELT_D1)
   double grid_d, grid_S, grid_total;
   double red[128];
-  double recbuf[16];                 // tuned kernel: the next step's record, staged by cp.async
+  double recbuf[2][24];              // tuned kernel: the records of the current and of the next step (cp.async)
   long long it, steps, node_steps, resmin1, resmin2;
   unsigned long long hash;
   int n1, n2, gap, nr1, nr2, Fl, status, warn, bc0, bc1, hidx, arrhenius;
@@ -496,6 +500,7 @@ __device__ inline void chain_build(Scal &Sh, const KArgs &A, const MemberPtrs &P
     r[REC_DT] = dt; r[REC_T] = t; r[REC_KD] = KD; r[REC_TEMP] = Tt; r[REC_DL] = D_l; r[REC_DR] = D_r;
     r[REC_RI1] = Rnew; r[REC_NR1] = (double)nr1; r[REC_NR2] = (double)nr2; r[REC_STATUS] = (double)rc;
     r[REC_WARN] = 0.0; r[REC_IT] = (double)(c.it + 1); r[REC_D] = rc ? 0.0 : d; r[REC_R] = 0.0;
+    r[REC_N1S] = (double)n1s; r[REC_N2S] = (double)n2s;
     c.count += 1;
     c.steps += 1;
     c.it += 1;
