@@ -428,6 +428,10 @@ struct ChainEnv {
   long long resmin1, resmin2;
   int arrhenius;
 };
+// SPLIT (constant diffusivities only: with an Arrhenius law D(T(t)) feeds dt): the history lookup of a step - KD(t),
+// T(t), their range checks - does not enter the recurrence, so thread 0 runs the recurrence alone and the records'
+// parameter fields are filled one record per thread afterwards (chain_params_record).
+template <bool SPLIT = false>
 __device__ inline void chain_build(Scal &Sh, const KArgs &A, const MemberPtrs &P, double *recs, int maxrec, int capL,
                                    int capR, int capS, int capPhase) {
   ChainEnv S;
@@ -444,7 +448,7 @@ __device__ inline void chain_build(Scal &Sh, const KArgs &A, const MemberPtrs &P
   const int dt_mode = A.dt_mode;
   const long long max_steps = A.max_steps;
   HistCache h;
-  hist_load(h, P, c.hidx);
+  if (!SPLIT) hist_load(h, P, c.hidx);
   while (c.count < maxrec) {
     if (c.status != 0 || !(c.t < S.t_tot) || (max_steps > 0 && c.steps >= max_steps)) { c.done = 1; break; }
     // ---- dt (find_dt functions.jl:465-490 / C1.jl:93) and update_time! (:1442-1450)
@@ -462,9 +466,10 @@ __device__ inline void chain_build(Scal &Sh, const KArgs &A, const MemberPtrs &P
     }
     double t = xadd(c.t, dt);
     if (t > S.t_tot) { dt = xsub(dt, xsub(t, S.t_tot)); t = S.t_tot; }
-    double KD, Tt, D_l, D_r;
-    int rc = chain_update_params(S, A, P, t, h, &KD, &Tt, &D_l, &D_r);
-    const int cur = h.i;
+    double KD = 0.0, Tt = 0.0, D_l = c.D_l, D_r = c.D_r;
+    int rc = 0;
+    if (!SPLIT) rc = chain_update_params(S, A, P, t, h, &KD, &Tt, &D_l, &D_r);
+    const int cur = SPLIT ? c.hidx : h.i;
     // ---- advect_interface_regrid! (functions.jl:29-64) on scalars
     const double Rnew = xadd(c.Ri1, xmul(V, dt));
     int n1s = c.n1, n2s = c.n2;
@@ -515,6 +520,36 @@ __device__ inline void chain_build(Scal &Sh, const KArgs &A, const MemberPtrs &P
     c.n1 = (int)nr1; c.n2 = (int)nr2;
   }
   Sh.ch = c;
+}
+
+// second pass of the split chain, one record per thread: update_t_dependent_param! (functions.jl:1350-1378) of the
+// record's time.  The interval is the first one with t_ar[i] <= t <= t_ar[i+1] (linear_interpolation_1D, :565-585),
+// found by bisection instead of the cursor walk; same arithmetic.  A failure here (KD / T / time outside the history)
+// comes before the step's interface checks in the reference's order, so it replaces whatever status pass one left.
+__device__ inline void chain_params_record(const Scal &S, const KArgs &A, const MemberPtrs &P, double *r) {
+  const double t = r[REC_T];
+  int rc = 0;
+  double KD = 0.0, Tt = 0.0;
+  if (t < S.tmin || t > S.tmax) rc = 6;
+  else {
+    int lo = 0, hi = A.hist_len - 2;                      // smallest i with t <= t_ar[i + 1]
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (t <= P.t_ar[mid + 1]) hi = mid; else lo = mid + 1; }
+    HistCache h;
+    hist_load(h, P, lo);
+    const double N2 = xmul(xsub(t, h.x0), h.iv);
+    const double N1 = xsub(1.0, N2);
+    KD = xadd(xmul(N1, h.k0), xmul(N2, h.k1));
+    Tt = xadd(xmul(N1, h.T0), xmul(N2, h.T1));
+    if (t == S.t_tot) {
+      Tt = P.T_ar[A.hist_len - 1];
+      KD = P.KD_ar[A.hist_len - 1];
+    } else {
+      if (KD < S.KDmin - 1e-12 || KD > S.KDmax + 1e-12) rc = 4;
+      else if (Tt < S.Tmin - 1e-12 || Tt > S.Tmax + 1e-12) rc = 5;
+    }
+  }
+  r[REC_KD] = KD; r[REC_TEMP] = Tt; r[REC_DL] = S.Di0; r[REC_DR] = S.Di1;
+  if (rc) { r[REC_STATUS] = (double)rc; r[REC_D] = 0.0; }
 }
 
 // ---- pchip slope at node i of one phase (functions.jl:786-806; value code, contraction allowed) ------
