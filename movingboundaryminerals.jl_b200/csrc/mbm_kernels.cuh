@@ -74,7 +74,6 @@ struct Scal {
   double lp0, lp1, lp2, lp3, lp4;    // parameters of the in-loop material law (MBM_LAW_OLIVINE_MELT_D1)
   double grid_d, grid_S, grid_total;
   double red[128];
-  double recbuf[2][24];              // tuned kernel: the records of the current and of the next step (cp.async)
   long long it, steps, node_steps, resmin1, resmin2;
   unsigned long long hash;
   int n1, n2, gap, nr1, nr2, Fl, status, warn, bc0, bc1, hidx, arrhenius;
