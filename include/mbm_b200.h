@@ -239,6 +239,40 @@ int mbm_calc_mass_vol(int32_t n_members, int32_t ndim, int32_t cap_left, int32_t
                       const double *C_right, const int64_t *res, const double *rho,
                       double *Mass /*[M]*/);
 
+/* ---- validation layer ---------------------------------------------
+ * The known-answer gates of the reference's own tests, evaluated per member from the ensemble's
+ * state so that a sweep of thousands of members is checked where it lives (MBM_FLAG_DEVICE_POINTERS:
+ * nothing but [M] results crosses the host link).  Quantities are in the units of the state arrays
+ * (the gates are ratios, invariant under the `scaling` of functions.jl:988-1008).
+ *   MBM_VAL_MASS_ERR  calc_mass_err (functions.jl:183-187) on calc_mass_vol (:205-212) of the state:
+ *                     out = (Mass, Mass0), relerr = (Mass - Mass0) * inv(Mass0)   [signed, as the reference]
+ *   MBM_VAL_RAYLEIGH  test/test_C1.jl: rayleigh_fractionation (Benchmarks.jl:239-260, with the as-shipped
+ *                     LinearIndices post-processing of :250-258) and the two trapezoidal integrals;
+ *                     out = (int_Ray, int_model), relerr = |a - b| / max(|a|, |b|)  [isapprox, rtol]
+ *   MBM_VAL_SMITH     test/test_B5.jl: smith (Benchmarks.jl:284-301, n = 1) against C_right;
+ *                     out = (||Can - C_right||_2, max(||Can||_2, ||C_right||_2)), relerr = their ratio */
+enum { MBM_VAL_MASS_ERR = 0, MBM_VAL_RAYLEIGH = 1, MBM_VAL_SMITH = 2 };
+typedef struct mbm_validate_args {
+  int32_t abi_version;   /* MBM_ABI_VERSION                                                   */
+  int32_t n_members, ndim, cap_left, cap_right, kind;
+  uint32_t flags;        /* MBM_FLAG_DEVICE_POINTERS: every pointer below is device memory     */
+  int32_t device;        /* CUDA device to run on                                             */
+  const double *x_left, *C_left, *x_right, *C_right;   /* state, as in mbm_couple_io          */
+  const int64_t *res;    /* [2,M]                                                             */
+  const double *Ri;      /* [2,M]                                                             */
+  const double *rho;     /* [2,M]  MASS_ERR                                                   */
+  const double *Mass0;   /* [M]    MASS_ERR                                                   */
+  const double *Ri0;     /* [2,M]  RAYLEIGH: radii at t = 0                                   */
+  const double *C0_r;    /* [M]    RAYLEIGH: C0_r[end], initial composition of the right phase */
+  const double *KD0;     /* [M]    RAYLEIGH, SMITH                                            */
+  const double *Di_r;    /* [M]    SMITH: Di[2]                                               */
+  const double *V_ip;    /* [M]    SMITH                                                      */
+  const double *t_tot;   /* [M]    SMITH: the time reached                                    */
+  double *out;           /* [2,M]  see the kind                                               */
+  double *relerr;        /* [M]                                                               */
+} mbm_validate_args;
+int mbm_validate_batch(const mbm_validate_args *);
+
 /* CUDA library only: seconds spent in the last call's kernels on device_ids[0], measured
  * with CUDA events on the launching stream (0 for the oracle), and the number of kernel
  * launches of the last call.                                                               */

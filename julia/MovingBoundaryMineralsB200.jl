@@ -44,6 +44,35 @@ struct CoupleIO                    # mbm_couple_io
     node_steps::Ptr{Int64}; rec::Ptr{Float64}
 end
 
+struct ValidateArgs                # mbm_validate_args
+    abi_version::Int32; n_members::Int32; ndim::Int32; cap_left::Int32; cap_right::Int32; kind::Int32
+    flags::UInt32; device::Int32
+    x_left::Ptr{Float64}; C_left::Ptr{Float64}; x_right::Ptr{Float64}; C_right::Ptr{Float64}
+    res::Ptr{Int64}; Ri::Ptr{Float64}; rho::Ptr{Float64}; Mass0::Ptr{Float64}; Ri0::Ptr{Float64}
+    C0_r::Ptr{Float64}; KD0::Ptr{Float64}; Di_r::Ptr{Float64}; V_ip::Ptr{Float64}; t_tot::Ptr{Float64}
+    out::Ptr{Float64}; relerr::Ptr{Float64}
+end
+const VAL_MASS_ERR = Int32(0); const VAL_RAYLEIGH = Int32(1); const VAL_SMITH = Int32(2)
+
+"""
+    rayleigh_gate(x_left, C_left, x_right, C_right, res, Ri, Ri0, C0_r_end, KD0; n)
+
+test/test_C1.jl's gate for every member of an ensemble (`[cap, M]` state arrays as the batch calls return them):
+`(out[2, M], relerr[M])` with `out = (int_Ray, int_model)`; `relerr[m] <= 1e-4` is the reference's tolerance.
+"""
+function rayleigh_gate(x_left, C_left, x_right, C_right, res, Ri, Ri0, C0_r_end, KD0; n::Integer)
+    M = size(x_left, 2); out = zeros(2, M); relerr = zeros(M)
+    GC.@preserve x_left C_left x_right C_right res Ri Ri0 C0_r_end KD0 out relerr begin
+        va = Ref(ValidateArgs(ABI_VERSION, M, n, size(x_left, 1), size(x_right, 1), VAL_RAYLEIGH, 0, 0,
+                              pointer(x_left), pointer(C_left), pointer(x_right), pointer(C_right), pointer(res),
+                              pointer(Ri), C_NULL, C_NULL, pointer(Ri0), pointer(C0_r_end), pointer(KD0),
+                              C_NULL, C_NULL, C_NULL, pointer(out), pointer(relerr)))
+        rc = ccall((:mbm_validate_batch, LIB), Cint, (Ref{ValidateArgs},), va)
+        rc == 0 || error("mbm_validate_batch failed with rc = $rc")
+    end
+    return out, relerr
+end
+
 status_string(s::Integer) = unsafe_string(ccall((:mbm_status_string, LIB), Cstring, (Int32,), Int32(s)))
 
 """

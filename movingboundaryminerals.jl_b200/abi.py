@@ -87,11 +87,26 @@ class SimpleIO(C.Structure):
 
 
 # every symbol include/mbm_b200.h declares
+VAL_MASS_ERR, VAL_RAYLEIGH, VAL_SMITH = 0, 1, 2   # mbm_validate_args.kind
+
+
+class ValidateArgs(C.Structure):
+    """mbm_validate_args: the known-answer gates of the reference's tests, per member (include/mbm_b200.h)"""
+    _fields_ = [
+        ("abi_version", C.c_int32), ("n_members", C.c_int32), ("ndim", C.c_int32), ("cap_left", C.c_int32),
+        ("cap_right", C.c_int32), ("kind", C.c_int32), ("flags", C.c_uint32), ("device", C.c_int32),
+        ("x_left", _dp), ("C_left", _dp), ("x_right", _dp), ("C_right", _dp), ("res", _i64p), ("Ri", _dp),
+        ("rho", _dp), ("Mass0", _dp), ("Ri0", _dp), ("C0_r", _dp), ("KD0", _dp), ("Di_r", _dp), ("V_ip", _dp),
+        ("t_tot", _dp), ("out", _dp), ("relerr", _dp),
+    ]
+
+
 ABI_SYMBOLS = [
     "mbm_version", "mbm_device_count", "mbm_backend", "mbm_status_string",
     "mbm_simple_diff_batch", "mbm_couple_flux_batch", "mbm_couple_mb_batch",
     "mbm_stefan_xt_batch", "mbm_couple_batch", "mbm_create_grid", "mbm_calc_mass_vol",
     "mbm_last_kernel_seconds", "mbm_last_kernel_launches", "mbm_set_stream", "mbm_measure_dfma_tflops",
+    "mbm_validate_batch",
 ]
 
 PKG_DIR = Path(__file__).resolve().parent
@@ -127,6 +142,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.mbm_set_stream.argtypes = [C.c_void_p]
     lib.mbm_measure_dfma_tflops.restype = C.c_double
     lib.mbm_measure_dfma_tflops.argtypes = [C.c_int]
+    lib.mbm_validate_batch.restype = C.c_int
+    lib.mbm_validate_batch.argtypes = [C.POINTER(ValidateArgs)]
     return lib
 
 

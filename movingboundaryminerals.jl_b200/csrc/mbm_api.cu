@@ -13,6 +13,7 @@
 
 #include "../../include/mbm_b200.h"
 #include "mbm_kernel_stream.cuh"
+#include "mbm_validate.cuh"
 
 namespace {
 
@@ -898,6 +899,51 @@ int mbm_calc_mass_vol(int32_t M, int32_t ndim, int32_t capL, int32_t capR, const
   st.release();
   cudaStreamSynchronize(st.stream);
   cudaStreamDestroy(st.stream);
+  return rc;
+}
+
+// validation layer: host or device pointers, one thread per member (not a hot path)
+int mbm_validate_batch(const mbm_validate_args *a) {
+  if (!a || a->abi_version != MBM_ABI_VERSION) return MBM_RC_BAD_ARG;
+  if (a->n_members < 0 || a->cap_left < 3 || a->cap_right < 3 || a->ndim < 1 || a->ndim > 3) return MBM_RC_BAD_ARG;
+  if (a->kind < MBM_VAL_MASS_ERR || a->kind > MBM_VAL_SMITH) return MBM_RC_BAD_ARG;
+  if (!a->x_left || !a->C_left || !a->x_right || !a->C_right || !a->res || !a->Ri || !a->out || !a->relerr) return MBM_RC_BAD_ARG;
+  if (a->kind == MBM_VAL_MASS_ERR && (!a->rho || !a->Mass0)) return MBM_RC_BAD_ARG;
+  if (a->kind == MBM_VAL_RAYLEIGH && (!a->Ri0 || !a->C0_r || !a->KD0)) return MBM_RC_BAD_ARG;
+  if (a->kind == MBM_VAL_SMITH && (!a->KD0 || !a->Di_r || !a->V_ip || !a->t_tot || a->ndim != 1)) return MBM_RC_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return MBM_RC_NO_DEVICE;
+  if (a->device < 0 || a->device >= ndev) return MBM_RC_NO_DEVICE;
+  if (a->n_members == 0) return 0;
+  DeviceScope dev_scope(a->device);
+  if (dev_scope.rc) return dev_scope.rc;
+  Stage st;
+  st.device_ptrs = (a->flags & MBM_FLAG_DEVICE_POINTERS) != 0;
+  const bool own_stream = !g_have_user_stream;
+  if (own_stream) CK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+  else st.stream = g_user_stream;
+  const size_t n = (size_t)a->n_members, capL = a->cap_left, capR = a->cap_right;
+  mbm::VArgs V;
+  memset(&V, 0, sizeof(V));
+  V.M = a->n_members; V.ndim = a->ndim; V.capL = a->cap_left; V.capR = a->cap_right; V.kind = a->kind;
+  V.x_left = st.in(a->x_left, n * capL); V.C_left = st.in(a->C_left, n * capL);
+  V.x_right = st.in(a->x_right, n * capR); V.C_right = st.in(a->C_right, n * capR);
+  V.res = (const long long *)st.in(a->res, 2 * n);
+  V.Ri = st.in(a->Ri, 2 * n);
+  V.rho = st.in(a->rho, 2 * n); V.Mass0 = st.in(a->Mass0, n);
+  V.Ri0 = st.in(a->Ri0, 2 * n); V.C0_r = st.in(a->C0_r, n); V.KD0 = st.in(a->KD0, n);
+  V.Di_r = st.in(a->Di_r, n); V.V_ip = st.in(a->V_ip, n); V.t_tot = st.in(a->t_tot, n);
+  V.out = st.outonly(a->out, 2 * n); V.relerr = st.outonly(a->relerr, n);
+  int rc = st.rc;
+  if (!rc) {
+    mbm::mbm_validate_kernel<<<(a->n_members + 63) / 64, 64, 0, st.stream>>>(V);
+    rc = launch_rc("validation kernel", cudaGetLastError());
+  }
+  if (!rc) rc = st.copy_back();
+  const bool async = g_have_user_stream && st.device_ptrs;
+  if (!rc && !async && cudaStreamSynchronize(st.stream) != cudaSuccess) rc = MBM_RC_CUDA;
+  st.release();
+  if (own_stream) { cudaStreamSynchronize(st.stream); cudaStreamDestroy(st.stream); }
   return rc;
 }
 

@@ -191,6 +191,28 @@ class CoupleEnsemble:
             raise RuntimeError(f"mbm_calc_mass_vol failed rc={rc}")
         return out
 
+    def validate(self, lib, kind, Ri0=None, C0_r=None, KD0=None, Di_r=None, V_ip=None, t_tot=None, device=0):
+        """mbm_validate_batch on the ensemble's state: (out[M,2], relerr[M]).  kind = abi.VAL_MASS_ERR (calc_mass_err of
+        calc_mass_vol against Mass0), abi.VAL_RAYLEIGH (test_C1.jl's gate; needs Ri0[M,2], C0_r[M], KD0[M]) or
+        abi.VAL_SMITH (test_B5.jl's gate, n = 1; needs KD0, Di_r, V_ip, t_tot [M], in the units of the state)."""
+        a = self.arrays
+        keep = []
+        def dp(v):
+            if v is None:
+                return None
+            v = np.ascontiguousarray(v, dtype=np.float64); keep.append(v)
+            return abi.dptr(v)
+        out = np.zeros((self.M, 2), dtype=np.float64); err = np.zeros(self.M, dtype=np.float64)
+        va = abi.ValidateArgs(abi.ABI_VERSION, self.M, self.ndim, self.cap_left, self.cap_right, kind, 0, device)
+        va.x_left, va.C_left, va.x_right, va.C_right = (abi.dptr(a[k]) for k in ("x_left", "C_left", "x_right", "C_right"))
+        va.res = abi.i64ptr(a["res"]); va.Ri = abi.dptr(a["Ri"]); va.rho = abi.dptr(a["rho"]); va.Mass0 = abi.dptr(a["Mass0"])
+        va.Ri0, va.C0_r, va.KD0, va.Di_r, va.V_ip, va.t_tot = dp(Ri0), dp(C0_r), dp(KD0), dp(Di_r), dp(V_ip), dp(t_tot)
+        va.out, va.relerr = abi.dptr(out), abi.dptr(err)
+        rc = lib.mbm_validate_batch(C.byref(va))
+        if rc != 0:
+            raise RuntimeError(f"mbm_validate_batch failed rc={rc}")
+        return out, err
+
     def member(self, m):
         """(x_left, C_left, x_right, C_right) views trimmed to the member's node counts."""
         a = self.arrays

@@ -1166,3 +1166,99 @@ double mbm_oracle_pow_int(double x, int64_t n) { return jl_pow_int(x, n); }
 void mbm_oracle_scan(const double *v, int64_t n, double *out, int op, int julia) {
   if (julia && op == 0) cumsum_julia(v, n, out); else scan_canonical(v, n, out, op);
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Validation layer: the known-answer gates of the reference's tests,   */
+/* per member, from the ensemble's state.                                                      */
+/* ------------------------------------------------------------------------------------------ */
+/* LinRange(a, b, n)[i] (0-based): Julia's lerpi, (1 - t)*a + t*b with t = i/(n - 1) */
+static double linrange_val(double a, double b, int64_t n, int64_t i) {
+  double t = (double)i / (double)(n - 1);
+  return (1.0 - t) * a + t * b;
+}
+
+/* test/test_C1.jl:9-12 with rayleigh_fractionation, Benchmarks.jl:239-260 */
+static void validate_rayleigh(const double *xl, const double *cl, int64_t n1, const double Ri0[2], double Ri1,
+                              double C0r, double KD0, int ndim, double *int_Ray, double *int_model) {
+  /* Ray_Fs = LinRange(Ri0[1]/Ri0[2], Ri[1]/Ri0[2], 1000).^n; Ray_Cs = (1 - Fs)^(KD0 - 1)*C0_r[end]*KD0   :245-248 */
+  const double a = Ri0[0] * jl_inv(Ri0[1]), b = Ri1 * jl_inv(Ri0[1]);
+  double acc = 0.0, Fp = 0.0, Cp = 0.0;
+  for (int64_t i = 0; i < 1000; ++i) {
+    double Fs = pow_ndim(linrange_val(a, b, 1000, i), ndim);
+    double Cs = pow(1.0 - Fs, KD0 - 1.0) * C0r * KD0;
+    if (i > 0) { double v = 0.5 * (Fs - Fp) * (Cp + Cs); acc = (i == 1) ? v : acc + v; }   /* trapezoidal_integration */
+    Fp = Fs; Cp = Cs;
+  }
+  *int_Ray = acc;
+  /* post-processing :250-258 as shipped: indi = findall(x -> x > Ri0[1], x_left) and x_left[LinearIndices(indi)],
+   * i.e. the FIRST length(indi) nodes; prepended by (Ri0[1], C interpolated at Ri0[1])                          */
+  int64_t k = 0;
+  for (int64_t i = 0; i < n1; ++i) if (xl[i] > Ri0[0]) ++k;
+  double Cbc = NAN;
+  lin_interp_1d(xl, cl, n1, Ri0[0], &Cbc);
+  const double iR = jl_inv(Ri0[1]);
+  double xp = pow_ndim(Ri0[0] * iR, ndim), yp = Cbc;
+  acc = 0.0;
+  for (int64_t i = 0; i < k; ++i) {
+    double xq = pow_ndim(xl[i] * iR, ndim), yq = cl[i];
+    double v = 0.5 * (xq - xp) * (yp + yq);
+    acc = (i == 0) ? v : acc + v;
+    xp = xq; yp = yq;
+  }
+  *int_model = acc;
+}
+
+/* test/test_B5.jl with smith, Benchmarks.jl:284-301 (n = 1) */
+static void validate_smith(const double *xr, const double *cr, int64_t n2, double Ri1, double Dan, double tan_, double Kan,
+                           double R, double *ndiff, double *nref) {
+  const double ksi = 0.5 * pow(Dan * tan_, -0.5);
+  const double Can0 = cr[n2 - 1];
+  double sd = 0.0, sa = 0.0, sb = 0.0;
+  for (int64_t i = 0; i < n2; ++i) {
+    double xan = xr[i] - Ri1;
+    double Can = 1.0 + ((1.0 - Kan) * jl_inv(2.0 * Kan)) * exp(-R * jl_inv(Dan) * xan) * erfc(ksi * (xan - R * tan_))
+                 - 0.5 * erfc(ksi * (xan + R * tan_))
+                 + ((1.0 - Kan) * jl_inv(2.0)) * (1.0 * jl_inv(1.0 - Kan) - 1.0 * jl_inv(Kan))
+                   * exp(-(1.0 - Kan) * (R * jl_inv(Dan)) * (xan + Kan * R * tan_))
+                   * erfc(ksi * (xan + (2.0 * Kan - 1.0) * R * tan_));
+    Can = Can * Can0;
+    sd += (Can - cr[i]) * (Can - cr[i]); sa += Can * Can; sb += cr[i] * cr[i];
+  }
+  *ndiff = sqrt(sd);
+  *nref = sqrt(sa > sb ? sa : sb);
+}
+
+int mbm_validate_batch(const mbm_validate_args *a) {
+  if (!a || a->abi_version != MBM_ABI_VERSION) return MBM_RC_BAD_ARG;
+  if (a->n_members < 0 || a->cap_left < 3 || a->cap_right < 3 || a->ndim < 1 || a->ndim > 3) return MBM_RC_BAD_ARG;
+  if (a->kind < MBM_VAL_MASS_ERR || a->kind > MBM_VAL_SMITH) return MBM_RC_BAD_ARG;
+  if (a->flags & MBM_FLAG_DEVICE_POINTERS) return MBM_RC_UNSUPPORTED;
+  if (!a->x_left || !a->C_left || !a->x_right || !a->C_right || !a->res || !a->Ri || !a->out || !a->relerr) return MBM_RC_BAD_ARG;
+  if (a->kind == MBM_VAL_MASS_ERR && (!a->rho || !a->Mass0)) return MBM_RC_BAD_ARG;
+  if (a->kind == MBM_VAL_RAYLEIGH && (!a->Ri0 || !a->C0_r || !a->KD0)) return MBM_RC_BAD_ARG;
+  if (a->kind == MBM_VAL_SMITH && (!a->KD0 || !a->Di_r || !a->V_ip || !a->t_tot || a->ndim != 1)) return MBM_RC_BAD_ARG;
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int64_t m = 0; m < a->n_members; ++m) {
+    const double *xl = a->x_left + m * a->cap_left, *cl = a->C_left + m * a->cap_left;
+    const double *xr = a->x_right + m * a->cap_right, *cr = a->C_right + m * a->cap_right;
+    const int64_t n1 = a->res[2 * m], n2 = a->res[2 * m + 1];
+    double o0 = NAN, o1 = NAN, e = NAN;
+    if (n1 >= 2 && n2 >= 2 && n1 <= a->cap_left && n2 <= a->cap_right) {
+      if (a->kind == MBM_VAL_MASS_ERR) {
+        const double rho[2] = { a->rho[2 * m], a->rho[2 * m + 1] };
+        o0 = calc_mass_vol(xl, xr, cl, cr, n1, n2, a->ndim, rho);
+        o1 = a->Mass0[m];
+        e = (o0 - o1) * jl_inv(o1);                                                       /* functions.jl:184 */
+      } else if (a->kind == MBM_VAL_RAYLEIGH) {
+        validate_rayleigh(xl, cl, n1, a->Ri0 + 2 * m, a->Ri[2 * m], a->C0_r[m], a->KD0[m], a->ndim, &o0, &o1);
+        const double den = fabs(o0) > fabs(o1) ? fabs(o0) : fabs(o1);
+        e = den > 0.0 ? fabs(o0 - o1) / den : 0.0;
+      } else {
+        validate_smith(xr, cr, n2, a->Ri[2 * m], a->Di_r[m], a->t_tot[m], a->KD0[m], a->V_ip[m], &o0, &o1);
+        e = o1 > 0.0 ? o0 / o1 : 0.0;
+      }
+    }
+    a->out[2 * m] = o0; a->out[2 * m + 1] = o1; a->relerr[m] = e;
+  }
+  return 0;
+}

@@ -1,0 +1,102 @@
+"""Validation layer (include/mbm_b200.h, mbm_validate_batch): the known-answer gates of the
+reference's tests evaluated per member by the library.  CPU part: the oracle's gates against the numpy restatement of
+src/Benchmarks.jl (tests/benchmarks_ref.py).  GPU part: the CUDA kernels against the oracle on the same states, and
+the reference's own tolerances (test_C1.jl, test_B5.jl: rtol 1e-4) on full runs through the CUDA path."""
+import numpy as np
+import pytest
+
+import benchmarks_ref as B
+from mbm_b200 import abi, drivers as d
+
+
+def _ensemble(lib, pars_list, steps):
+    ens, aux = d.build_couple_ensemble(pars_list, lib)
+    assert ens.run(lib, max_steps=steps, flags=abi.FLAG_MASS_FINAL) == 0
+    assert np.all(ens.status == 0), ens.status
+    return ens, aux
+
+
+def _c1_members():
+    out = []
+    for kd, ri in ((50.0, 0.01), (20.0, 0.015), (120.0, 0.008)):
+        p = d.pars_C1(); p.update(KD_ar=(kd, kd), Ri=[ri, 1.0], Cr_i=p["Cl_i"] / kd); out.append(p)
+    return out
+
+
+def _rayleigh_ref(ens, aux, m, n):
+    xl, cl, xr, cr = ens.member(m)
+    Fs, Fl, Cl, Cs, Clp, phi = B.rayleigh_fractionation(xl, cl, aux["Ri0"][m], ens.Ri[m], aux["C0_r"][m], aux["KD0"][m], n)
+    return B.trapezoidal_integration(Fs, Cs), B.trapezoidal_integration(phi ** n, Clp)
+
+
+def test_oracle_rayleigh_gate_matches_numpy(oracle):
+    pars = _c1_members()
+    ens, aux = _ensemble(oracle, pars, 400)
+    out, err = ens.validate(oracle, abi.VAL_RAYLEIGH, Ri0=np.array(aux["Ri0"]), C0_r=np.array([c[-1] for c in aux["C0_r"]]),
+                            KD0=aux["KD0"])
+    for m in range(len(pars)):
+        a, b = _rayleigh_ref(ens, aux, m, pars[m]["n"])
+        assert abs(out[m, 0] - a) <= 1e-12 * abs(a) and abs(out[m, 1] - b) <= 1e-12 * abs(b), (out[m], a, b)
+        assert abs(err[m] - abs(a - b) / max(abs(a), abs(b))) < 1e-12
+
+
+def test_oracle_smith_and_mass_gates_match_numpy(oracle):
+    p = d.pars_B5()
+    ens, aux = _ensemble(oracle, [p], 500)
+    a = ens.arrays
+    out, err = ens.validate(oracle, abi.VAL_SMITH, KD0=aux["KD0"], Di_r=a["Di"][:, 1], V_ip=a["V_ip"], t_tot=a["t"])
+    xl, cl, xr, cr = ens.member(0)
+    xan, Can = B.smith(xr, cr, ens.Ri[0], a["Di"][0], a["t"][0], aux["KD0"][0], a["V_ip"][0], 1)
+    ok, rel = B.isapprox(Can, cr, 1e-4)
+    assert abs(err[0] - rel) < 1e-12 * max(rel, 1.0), (err[0], rel)
+    out, err = ens.validate(oracle, abi.VAL_MASS_ERR)
+    assert out[0, 0] == a["Mass"][0] and out[0, 1] == a["Mass0"][0]            # calc_mass_vol of the state, bit for bit
+    assert err[0] == (a["Mass"][0] - a["Mass0"][0]) * (1.0 / a["Mass0"][0])     # calc_mass_err, functions.jl:184
+
+
+def test_validate_rejects_bad_arguments(oracle):
+    import ctypes as C
+    va = abi.ValidateArgs(abi.ABI_VERSION, 1, 1, 8, 8, 7, 0, 0)
+    assert oracle.mbm_validate_batch(C.byref(va)) == -1
+    cuda = abi.load_cuda_library()
+    assert cuda.mbm_validate_batch(C.byref(va)) == -1
+
+
+@pytest.mark.gpu
+def test_cuda_gates_match_oracle(oracle, cuda_lib):
+    pars = _c1_members()
+    eo, aux = _ensemble(oracle, pars, 400)
+    kw = dict(Ri0=np.array(aux["Ri0"]), C0_r=np.array([c[-1] for c in aux["C0_r"]]), KD0=aux["KD0"])
+    oo, eo_err = eo.validate(oracle, abi.VAL_RAYLEIGH, **kw)
+    og, eg_err = eo.validate(cuda_lib, abi.VAL_RAYLEIGH, **kw)                  # the same state through both libraries
+    assert np.allclose(oo, og, rtol=1e-12, atol=0) and np.allclose(eo_err, eg_err, rtol=1e-9, atol=1e-15)
+    oo, eo_err = eo.validate(oracle, abi.VAL_MASS_ERR)
+    og, eg_err = eo.validate(cuda_lib, abi.VAL_MASS_ERR)
+    assert np.array_equal(oo, og) and np.array_equal(eo_err, eg_err)            # same operations in the same order
+    p = d.pars_B5()
+    eb, auxb = _ensemble(oracle, [p], 500)
+    a = eb.arrays
+    kw = dict(KD0=auxb["KD0"], Di_r=a["Di"][:, 1], V_ip=a["V_ip"], t_tot=a["t"])
+    oo, eo_err = eb.validate(oracle, abi.VAL_SMITH, **kw)
+    og, eg_err = eb.validate(cuda_lib, abi.VAL_SMITH, **kw)
+    assert np.allclose(oo, og, rtol=1e-10, atol=0) and np.allclose(eo_err, eg_err, rtol=1e-9, atol=1e-15)
+
+
+@pytest.mark.gpu
+def test_reference_gates_on_full_runs_through_cuda(cuda_lib):
+    """test/test_C1.jl (Rayleigh, rtol 1e-4) and test/test_B5.jl (Smith, rtol 1e-4) for every member of a small sweep,
+    decided by the library from the final state"""
+    pars = _c1_members()
+    ens, aux = _ensemble(cuda_lib, pars, 0)
+    out, err = ens.validate(cuda_lib, abi.VAL_RAYLEIGH, Ri0=np.array(aux["Ri0"]),
+                            C0_r=np.array([c[-1] for c in aux["C0_r"]]), KD0=aux["KD0"])
+    assert np.all(err < 1e-4), err
+    pb = []
+    for kd in (0.1, 0.2):
+        p = d.pars_B5(); pb.append(p)
+    ens, aux = _ensemble(cuda_lib, pb, 0)
+    a = ens.arrays
+    out, err = ens.validate(cuda_lib, abi.VAL_SMITH, KD0=aux["KD0"], Di_r=a["Di"][:, 1], V_ip=a["V_ip"], t_tot=a["t"])
+    assert np.all(err < 1e-4), err
+    out, err = ens.validate(cuda_lib, abi.VAL_MASS_ERR)
+    assert np.all(np.isfinite(err))
