@@ -33,7 +33,7 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
-TRAFFIC_BYTES_8192 = 486.3e6 + 596.0e6     # ncu (profiles/r01_ncu_v2kernel_head_summary.txt), see roofline.traffic below
+TRAFFIC_BYTES_8192 = 605.6e6 + 736.5e6     # ncu (profiles/r02_ncu_v2kernel_summary.txt), see roofline.traffic below
 sys.path.insert(0, str(ROOT))
 
 
@@ -247,7 +247,7 @@ def main():
         dist.all_reduce(tns, op=dist.ReduceOp.SUM)
     secs_max, ns_all, bad_all = float(tsec.item()), float(tns[0].item()), int(tns[1].item())
     value = ns_all / secs_max
-    kernel_ms = 1e3 * secs / max(args.steps, 1)     # the tuned kernel is >99 % of a step (profiles/r01_ncu_launch_list.csv)
+    kernel_ms = 1e3 * secs / max(args.steps, 1)     # the tuned kernel is >99 % of a step (profiles/r02_ncu_launch_list.csv)
 
     # ---------------- e2e: host (pinned) buffers through the C ABI, copies inside the timed region -------------
     e2e = None
@@ -304,11 +304,11 @@ def main():
     roofline = {"bound": "fp64", "achieved": per_gpu * flops_per_ns * 1e-12, "peak": dfma, "unit": "TFLOP/s",
                 "frac": (per_gpu * flops_per_ns * 1e-12 / dfma) if dfma > 0 else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload (8192 members x 250 time steps),
-                # `ncu --set full` capture summarised in profiles/r01_ncu_v2kernel_head_summary.txt; scaled with the members
+                # `ncu --set full` capture summarised in profiles/r02_ncu_v2kernel_summary.txt; scaled with the members
                 "traffic": TRAFFIC_BYTES_8192 * args.members_per_gpu / 8192.0,
                 "peak_source": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "flops_per_node_step": flops_per_ns, "kernel": "mbm_step_kernel_v2<256,2>", "kernel_ms_per_launch": kernel_ms,
-                "traffic_note": "bytes per launch from ncu (486 MB read + 596 MB written at 8192 members, profiles/r01_ncu_v2kernel_head_summary.txt): the state and the histories cross HBM once per launch, not once per step (0.16 % of DRAM throughput); algorithmic streaming traffic would be 32 B x node-steps = 157 GB per launch",
+                "traffic_note": "bytes per launch from ncu (606 MB read + 737 MB written at 8192 members, profiles/r02_ncu_v2kernel_summary.txt): the state, the histories and the step records cross HBM once per launch, not once per step (0.3 % of DRAM throughput); algorithmic streaming traffic would be 32 B x node-steps = 157 GB per launch",
                 "hbm_view": {"bound": "hbm", "achieved": per_gpu * 32 * 1e-9, "peak": hbm, "unit": "GB/s",
                              "frac": per_gpu * 32 * 1e-9 / hbm, "bytes_per_node_step": 32,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",

@@ -171,6 +171,10 @@ int launch_T(const mbm::KArgs &A, int member0, int count, bool use_global, size_
   return launch_rc("general kernel launch", cudaGetLastError());
 }
 
+#ifndef MBM_DEV_FIXED_T
+#define MBM_DEV_FIXED_T 256
+#define MBM_DEV_FIXED_N 2
+#endif
 #ifndef MBM_V2_T
 #define MBM_V2_T 256
 #endif
@@ -204,8 +208,8 @@ int launch_fixed_TN(const mbm::KArgs &A, int member0, int count, size_t smem_byt
 }
 template <int T>
 int launch_fixed_T(const mbm::KArgs &A, int member0, int count, size_t smem_bytes, cudaStream_t s) {
-#ifdef MBM_DEV_MIN
-  if (T == 256 && A.ndim == 2) return launch_fixed_TN<256, 2>(A, member0, count, smem_bytes, s);
+#ifdef MBM_DEV_MIN   // A/B builds: one instantiation (MBM_DEV_FIXED_T threads, ndim MBM_DEV_FIXED_N; default 256, 2)
+  if (T == MBM_DEV_FIXED_T && A.ndim == MBM_DEV_FIXED_N) return launch_fixed_TN<MBM_DEV_FIXED_T, MBM_DEV_FIXED_N>(A, member0, count, smem_bytes, s);
   return MBM_RC_UNSUPPORTED;
 #else
   switch (A.ndim) {
@@ -246,7 +250,7 @@ int static_smem_of(K kern) {
 template <int T>
 int fixed_static_T(int ndim) {
 #ifdef MBM_DEV_MIN
-  return static_smem_of(mbm::mbm_fixed_kernel<256, 2>);
+  return static_smem_of(mbm::mbm_fixed_kernel<MBM_DEV_FIXED_T, MBM_DEV_FIXED_N>);
 #else
   switch (ndim) {
     case 1: return static_smem_of(mbm::mbm_fixed_kernel<T, 1>);
