@@ -434,3 +434,60 @@ def test_bad_arguments_are_rejected_before_any_launch(cuda_lib):
     assert cuda_lib.mbm_couple_batch(C.byref(common), C.byref(params), C.byref(io)) == -1
     params.law = 0
     assert cuda_lib.mbm_couple_batch(C.byref(common), C.byref(params), C.byref(io)) == 0   # the context is still healthy
+
+
+def test_run_ahead_chain_variants(oracle, cuda_lib):
+    """the tuned kernel's step records: (a) Arrhenius diffusivities with a moving interface keep the one-pass chain (D(T(t))
+    feeds dt), (b) constant diffusivities take the two-pass chain (recurrence by thread 0, history lookups one record per
+    thread, bisection instead of the cursor walk) - both against the oracle's step-by-step scalars, node counts changing on
+    the way ([60 90] nodes, large steps: rescans of the left mesh, runs that leave the aligned pattern)"""
+    # unscaled members: the reference's Arrhenius switch `Di == [-1 -1]` (functions.jl:1367) only fires when `scaling` has
+    # not divided Di by Dsc (B2 is unscaled for the same reason); D(1273 K) ~ [4e-7, 5e-8] as in the constant members
+    pa = d.pars_MB_growth(); pa.update(res=[60, 90], Di=[-1.0, -1.0], D0=[5.1e-3, 6.3e-4], R=8.314472, Ea1=1e5, Ea2=1e5,
+                                       T_ar=(1273.15, 1173.15), scale=False)
+    pb = d.pars_MB_growth(); pb.update(res=[60, 90], V_ip=2e-7, scale=False)
+    pc = d.pars_MB_growth(); pc.update(res=[60, 90], V_ip=-3e-7, KD_ar=(0.9, 0.3), scale=False)
+    eo, eg = run_both([pa, pb, pc], oracle, cuda_lib, 700)
+    assert np.all(eo.status == 0), eo.status
+    assert len({tuple(r) for r in eo.res}) > 1
+    compare(eo, eg, tol=2e-9)          # member 0: CUDA exp vs glibc exp (1-ulp D differences feed dt)
+    for m in (1, 2):
+        for a, b in zip(eo.member(m), eg.member(m)):
+            assert _relerr(a, b) < TOL
+
+
+def test_history_failures_inside_the_run_ahead_chain(oracle, cuda_lib):
+    """update_t_dependent_param!'s throw sites reached in the middle of a batch of step records: the time leaves the
+    history (functions.jl:571, status 6) - the member stops at the same step with the same t, dt, it as in the oracle,
+    the others go on"""
+    good = d.pars_MB_growth(); good.update(res=[60, 90])
+    bad = d.pars_MB_growth(); bad.update(res=[60, 90])
+    eo, _ = d.build_couple_ensemble([good, bad, good], oracle)
+    eg, _ = d.build_couple_ensemble([good, bad, good], cuda_lib)
+    for e in (eo, eg):                                  # member 1: its own, shorter history (ends after ~40 steps)
+        H = e.hist_len
+        for k in ("t_ar", "T_ar", "KD_ar"):
+            e.arrays[k] = np.repeat(e.arrays[k], 3, axis=0) if e.arrays[k].shape[0] == 1 else e.arrays[k]
+        e.arrays["t_ar"][1] = np.linspace(0.0, 40.0 * float(eo.arrays["t_ar"][0, -1]) / 9352.0, H)
+    assert eo.run(oracle, max_steps=200, flags=abi.FLAG_MASS_FINAL) == 0
+    assert eg.run(cuda_lib, max_steps=200, flags=abi.FLAG_MASS_FINAL) == 0
+    assert list(eo.status) == list(eg.status) and eo.status[1] == 6 and eo.status[0] == 0, (eo.status, eg.status)
+    for k in ("it", "res", "node_steps"):
+        assert np.array_equal(eo.arrays[k], eg.arrays[k]), k
+    assert _relerr(eo.t, eg.t) < 1e-13 and _relerr(eo.dt, eg.dt) < 1e-13
+    for m in range(3):
+        for a, b in zip(eo.member(m), eg.member(m)):
+            assert _relerr(a, b) < TOL
+
+
+def test_step_history_of_a_moving_couple(oracle, cuda_lib):
+    """MBM_FLAG_RECORD with the tuned kernel: per-step (Mass, T, KD, Ri[1]) - the `Mass` vector DCGF returns
+    (Diff_couple_1D_general_Flux.jl:137) - against the oracle"""
+    p = d.pars_MB_growth(); p.update(res=[60, 90], KD_ar=(0.9, 0.6))
+    eo, _ = d.build_couple_ensemble([p], oracle)
+    eg, _ = d.build_couple_ensemble([p], cuda_lib)
+    assert eo.run(oracle, max_steps=120, rec_cap=128) == 0 and eg.run(cuda_lib, max_steps=120, rec_cap=128) == 0
+    ro, rg = eo.arrays["rec"][0, :120], eg.arrays["rec"][0, :120]
+    assert np.all(ro[:, 0] > 0)
+    for c in range(4):
+        assert _relerr(ro[:, c], rg[:, c]) < 1e-11, c
