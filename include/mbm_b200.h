@@ -289,6 +289,12 @@ int64_t mbm_last_kernel_launches(void);
 int mbm_set_stream(void *cuda_stream);
 double mbm_measure_dfma_tflops(int device);
 
+/* CUDA library only (oracle: zeros).  Diagnostics of the streaming kernel for long uniform meshes
+ * (MRefin == 1, closed-form meshes): member-steps of `device` since the library was loaded that took the fused
+ * back-substitution + regrid pass / the two-pass path (node counts or layout changed by regrid!,
+ * functions.jl:873-889).  Tests use it to check which path ran.  Returns 0, or MBM_RC_CUDA.           */
+int mbm_stream_pass_counts(int device, uint64_t *fused_steps, uint64_t *twopass_steps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@
 
 #include "../../include/mbm_b200.h"
 #include "mbm_kernel_stream.cuh"
+#include "mbm_kernel_stream2.cuh"
 #include "mbm_validate.cuh"
 
 namespace {
@@ -227,6 +228,25 @@ int launch_stream_N(const mbm::KArgs &A, int member0, int count, cudaStream_t s)
   kern<<<count, 256, mbm::STG_BYTES, s>>>(A, member0);
   return launch_rc("streaming kernel launch", cudaGetLastError());
 }
+template <int NDIM>
+int launch_stream2_N(const mbm::KArgs &A, int member0, int count, cudaStream_t s) {
+  auto kern = mbm::mbm_stream2_kernel<256, NDIM>;
+  if (int rc = launch_rc("streaming kernel (closed-form meshes): shared-memory opt-in",
+                         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mbm::STG_BYTES))) return rc;
+  kern<<<count, 256, mbm::STG_BYTES, s>>>(A, member0);
+  return launch_rc("streaming kernel (closed-form meshes) launch", cudaGetLastError());
+}
+int launch_stream2(const mbm::KArgs &A, int member0, int count, cudaStream_t s) {
+#ifdef MBM_DEV_MIN
+  return launch_stream2_N<2>(A, member0, count, s);
+#else
+  switch (A.ndim) {
+    case 1: return launch_stream2_N<1>(A, member0, count, s);
+    case 2: return launch_stream2_N<2>(A, member0, count, s);
+    default: return launch_stream2_N<3>(A, member0, count, s);
+  }
+#endif
+}
 int launch_stream(const mbm::KArgs &A, int member0, int count, cudaStream_t s) {
 #ifdef MBM_DEV_MIN
   return launch_stream_N<2>(A, member0, count, s);
@@ -434,6 +454,14 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
     }
     if (use_stream) {
       AS.steps_done = A.steps_done; AS.only_deferred = A.only_deferred; AS.recs = A.recs;
+      // closed-form meshes first (only the concentrations cross HBM); members whose x arrays are not LinRanges are
+      // handed on (status -1) to the kernel that keeps x in memory
+      if (!getenv("MBM_NO_STREAM2")) {
+        rc = launch_stream2(AS, m0 + off, n, s);
+        if (rc) return rc;
+        ++launches;
+        AS.only_deferred = 1;
+      }
       rc = launch_stream(AS, m0 + off, n, s);
       if (rc) return rc;
       ++launches;
@@ -768,6 +796,19 @@ double mbm_measure_dfma_tflops(int device) {
   return best;
 }
 int64_t mbm_last_kernel_launches(void) { return g_last_kernel_launches_any; }
+int mbm_stream_pass_counts(int device, uint64_t *fused_steps, uint64_t *twopass_steps) {
+  int prev = 0;
+  if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) return MBM_RC_CUDA;
+  unsigned long long f = 0, t = 0;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(&f, mbm::g_s2_fused_steps, sizeof(f));
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(&t, mbm::g_s2_twopass_steps, sizeof(t));
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) return MBM_RC_CUDA;
+  if (fused_steps) *fused_steps = f;
+  if (twopass_steps) *twopass_steps = t;
+  return 0;
+}
 
 const char *mbm_status_string(int32_t s) {
   switch (s) {

@@ -491,3 +491,56 @@ def test_step_history_of_a_moving_couple(oracle, cuda_lib):
     assert np.all(ro[:, 0] > 0)
     for c in range(4):
         assert _relerr(ro[:, c], rg[:, c]) < 1e-11, c
+
+
+def _stream_pass_counts(lib):
+    import ctypes as C
+    f, t = C.c_uint64(0), C.c_uint64(0)
+    assert lib.mbm_stream_pass_counts(0, C.byref(f), C.byref(t)) == 0
+    return int(f.value), int(t.value)
+
+
+def test_streaming_closed_form_fused_pass(oracle, cuda_lib):
+    """streaming kernel for uniform meshes (MRefin = 1): meshes recomputed from the LinRange closed form, back-substitution
+    and regrid in one pass where the node counts stay (growth members at config 5's shape: nr = resmin) and the two-pass
+    path where regrid! changes them (resorption: nr[2] jumps from 5000 to 7455 at the first step) - both against the
+    oracle, integers and the regrid checksum exact"""
+    pars = []
+    for V, res, r in ((1e-7, [5000, 5000], 0.45), (2e-7, [4200, 4200], 0.41), (-1e-7, [4100, 5000], 0.45),
+                      (1.5e-7, [5001, 5003], 0.48)):
+        p = d.pars_MB_growth()
+        p.update(V_ip=V, res=res, MRefin=1.0, Ri=[r, 1.0], t_tot=2e4, KD_ar=(0.1, 0.1), Cl_i=0.5, Cr_i=5.0)
+        pars.append(p)
+    eo, _ = d.build_couple_ensemble(pars, oracle, cap_left=9500, cap_right=9500)
+    eg, _ = d.build_couple_ensemble(pars, cuda_lib, cap_left=9500, cap_right=9500)
+    f0, t0 = _stream_pass_counts(cuda_lib)
+    assert eo.run(oracle, max_steps=60) == 0
+    assert eg.run(cuda_lib, max_steps=60, flags=abi.FLAG_FORCE_STREAMING) == 0
+    f1, t1 = _stream_pass_counts(cuda_lib)
+    assert f1 - f0 >= 4 * 55, (f1 - f0, t1 - t0)          # every step whose node counts stay
+    assert t1 - t0 >= 1, (f1 - f0, t1 - t0)               # the resorption member's first step
+    compare(eo, eg)
+    # split calls resume on the closed form (the x arrays a call returns are the LinRanges the next one verifies)
+    eg2, _ = d.build_couple_ensemble(pars, cuda_lib, cap_left=9500, cap_right=9500)
+    for _ in range(3):
+        assert eg2.run(cuda_lib, max_steps=20, flags=abi.FLAG_FORCE_STREAMING) == 0
+    f2, _t2 = _stream_pass_counts(cuda_lib)
+    assert f2 - f1 >= 3 * 50
+    for k in ("x_left", "x_right", "C_left", "C_right", "res", "it", "idx_hash", "node_steps"):
+        assert np.array_equal(eg.arrays[k], eg2.arrays[k]), k
+
+
+def test_streaming_other_meshes_take_the_first_kernel(oracle, cuda_lib):
+    """a member whose x arrays are not the LinRange pair (one node perturbed by an ulp) is handed to the streaming kernel
+    that keeps x in memory; results still match the oracle on the same input"""
+    p = d.pars_MB_growth()
+    p.update(V_ip=1e-7, res=[3000, 3000], MRefin=1.0, Ri=[0.45, 1.0], t_tot=2e4, KD_ar=(0.1, 0.1), Cl_i=0.5, Cr_i=5.0)
+    eo, _ = d.build_couple_ensemble([p], oracle, cap_left=3100, cap_right=3100)
+    eg, _ = d.build_couple_ensemble([p], cuda_lib, cap_left=3100, cap_right=3100)
+    for e in (eo, eg):
+        e.arrays["x_left"][0, 1500] = np.nextafter(e.arrays["x_left"][0, 1500], 1.0)
+    f0, t0 = _stream_pass_counts(cuda_lib)
+    assert eo.run(oracle, max_steps=10) == 0
+    assert eg.run(cuda_lib, max_steps=10, flags=abi.FLAG_FORCE_STREAMING) == 0
+    assert _stream_pass_counts(cuda_lib) == (f0, t0)
+    compare(eo, eg)
