@@ -24,6 +24,7 @@
 // Traffic per node-step: forward sweep reads C, writes A, G, R (32 B); fused pass reads A, G, R, writes the new C (32 B):
 // 64 B against the 104 B of the first streaming kernel (algorithmic figure, SURVEY.md §8(d): 32 B with x, 16 B without).
 #pragma once
+#include <type_traits>
 #include "mbm_kernel_stream.cuh"
 
 namespace mbm {
@@ -236,8 +237,11 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
   }
   const int MC = A.kcapL;
   const size_t ASZ = (size_t)MC * T;
-  double *base = A.workspace + (size_t)blockIdx.x * 6 * ASZ;        // the first streaming kernel's workspace (6 arrays)
-  double *C = base, *FA = base + ASZ, *FG = base + 2 * ASZ, *Cn = base + 3 * ASZ;
+  // the first streaming kernel's workspace (6 arrays per member): the state C, the regrid's output Cn, and the rows of
+  // the elimination interleaved row by row, RAG[(3 k + a) T + t], a = 0: R, 1: A (fill-in), 2: G - one row pointer and
+  // immediate offsets for the stores of the forward sweep, one bulk copy per batch for the second pass
+  double *base = A.workspace + (size_t)blockIdx.x * 6 * ASZ;
+  double *C = base, *Cn = base + ASZ, *const RAG = base + 2 * ASZ;
   const int bc = A.inner_bc;
   const bool mb = (bc == BC_MB);
   MemberPtrs P;
@@ -475,20 +479,23 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
         if (mb) hprev = 0.5 * fabs(Vs - powd<NDIM>(x_halo_prev));
       }
       bA = 0.0; bR = 0.0;
-      auto fwd_row = [&](const int k, const size_t a, const double x_next, const double c_next) {
-        const bool last = (k == len - 1);
+      // one row of the sweep (k: row of the column), given the next node's x and C; rows go to pr[0] (R), pr[T] (A), pr[2T] (G).
+      // INTERIOR rows (neither the first nor the last row of the column) carry no tests of k.
+      auto fwd_row = [&](auto interior, const int k, double *pr, const double x_next, const double c_next) {
+        constexpr bool INT = decltype(interior)::value;
+        const bool first = INT ? false : (k == 0), last = INT ? false : (k == len - 1);
         double Aself, A12, Anext, kk;
         elem_mats_dir<NDIM>(x_self, x_next, Dsd, idts, Aself, A12, Anext, kk);
         double diag = (Aself - kk) + dcar;
         double rhs = fma(Aself, c_self, A12 * c_next) + rcar;
         const double sup_true = A12 + kk;
         double sup = sup_true;
-        if (k == 0 && dir0) { diag = 1.0; rhs = Co_out; sup = 0.0; sub = 0.0; }
+        if (first && dir0) { diag = 1.0; rhs = Co_out; sup = 0.0; sub = 0.0; }
         const double inv = frcp_(diag - sub * Gp);
-        const double An = (k == 0) ? (sub * inv) : (-sub * Ap * inv);
+        const double An = first ? (sub * inv) : (-sub * Ap * inv);
         const double Gn = sup * inv;
         const double Rn = (rhs - sub * Rp) * inv;
-        FA[a] = An; FG[a] = Gn; C[a] = Rn;
+        pr[0] = Rn; pr[T] = An; pr[2 * T] = Gn;
         if (!last) { bR = fma(pi, Rn, bR); bA = fma(pi, An, bA); pi = -pi * Gn; }
         if (mb) {
           const double Vn = powd<NDIM>(x_next);
@@ -518,19 +525,30 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
           stg_par ^= 1u << buf;
           const double *cs_ = stg + (size_t)buf * (STG_R * T) + tid;
           const int k0 = b * STG_R, nr = min(STG_R, nrows - k0);
-#pragma unroll 1
-          for (int rr = 0; rr < nr; ++rr) {
-            const int k = k0 + rr;
-            if (k < len) {
-              const bool last = (k == len - 1);
+          double *const pr0 = RAG + (size_t)k0 * (3 * T) + tid;
+          if (nr == STG_R && k0 >= 1 && k0 + STG_R <= len - 1) {
+            // a batch of interior rows: straight-line code, immediate offsets
+#pragma unroll
+            for (int rr = 0; rr < STG_R; ++rr) {
               const double xn_ = s2_lerp(MO, fi);
               fi += MO.s;
-              fwd_row(k, (size_t)k * T + tid, last ? x_halo_next : xn_, last ? c_halo_next : cs_[rr * T]);
+              fwd_row(std::true_type{}, k0 + rr, pr0 + rr * (3 * T), xn_, cs_[rr * T]);
+            }
+          } else {
+#pragma unroll 1
+            for (int rr = 0; rr < nr; ++rr) {
+              const int k = k0 + rr;
+              if (k < len) {
+                const bool last = (k == len - 1);
+                const double xn_ = s2_lerp(MO, fi);
+                fi += MO.s;
+                fwd_row(std::false_type{}, k, pr0 + rr * (3 * T), last ? x_halo_next : xn_, last ? c_halo_next : cs_[rr * T]);
+              }
             }
           }
           __syncthreads();
         }
-        if (len == m) fwd_row(m - 1, (size_t)(m - 1) * T + tid, x_halo_next, c_halo_next);
+        if (len == m) fwd_row(std::false_type{}, m - 1, RAG + (size_t)(m - 1) * (3 * T) + tid, x_halo_next, c_halo_next);
       }
       bG = -pi;
     }
@@ -588,12 +606,9 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
     const int nrows_b = m - 1, nbatch_b = (nrows_b + STG_R - 1) / STG_R;
     auto issue_b = [&](const int b) {
       const int hi = m - 2 - b * STG_R, lo = max(hi - STG_R + 1, 0), nr = hi - lo + 1, buf = b % STG_NBB;
-      const unsigned bytes = (unsigned)nr * T * 8u;
-      double *dst = stg + (size_t)buf * (3 * STG_R * T);
-      mbar_expect_tx(&fullb[buf], 3u * bytes);
-      bulk_g2s(dst, C + (size_t)lo * T, bytes, &fullb[buf]);
-      bulk_g2s(dst + STG_R * T, FA + (size_t)lo * T, bytes, &fullb[buf]);
-      bulk_g2s(dst + 2 * STG_R * T, FG + (size_t)lo * T, bytes, &fullb[buf]);
+      const unsigned bytes = (unsigned)nr * 3u * T * 8u;
+      mbar_expect_tx(&fullb[buf], bytes);
+      bulk_g2s(stg + (size_t)buf * (3 * STG_R * T), RAG + (size_t)lo * (3 * T), bytes, &fullb[buf]);
     };
 
     bool fused_done = false;
@@ -608,7 +623,7 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
       bool ok = true;
       double cn = sj;
       double x1 = 0.0, x2 = 0.0, y1 = sj, ih12 = 1.0, M12 = 0.0, D2 = 0.0;
-      double fio = 0.0;                                      // LinRange index of the next row's old node
+      double fio = 0.0, fin = 0.0;                           // LinRange indices of the next row's old node / new node
       if (active) {
         const int k = len - 1;
         if (k < 4) sh[k][tid] = cn;
@@ -617,7 +632,36 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
         x2 = (f + len == no - 1) ? Rnew : s2_at(MO, f + len);
         ih12 = frcp_(x2 - x1);
         fio = MO.fi0 + MO.s * (double)(f + len - 2);
+        fin = MN.fi0 + MN.s * (double)(f + len - 1 - o);     // new node of row len - 2
       }
+      // one row (k) of the walk: back-substitute old node q = f + k, complete the stencil of old interval [q + 1, q + 2]
+      // and evaluate its new node pn = q + 1 - o into *pc.  rp: the row's (R, A, G) in the staging buffer.  INTERIOR rows
+      // (4 <= k <= kI_hi) publish nothing and always evaluate.
+      auto frow = [&](auto interior, const int k, const double *rp, double *pc) {
+        constexpr bool INT = decltype(interior)::value;
+        cn = rp[0] - rp[T] * spv - rp[2 * T] * cn;           // solved value of old node q
+        if (!INT) {
+          if (k < 4) sh[k][tid] = cn;
+          if (k >= len - 4) sh[4 + (k - (len - 4))][tid] = cn;
+        }
+        const double x0 = s2_lerp(MO, fio);
+        fio -= MO.s;
+        const double Xj = s2_lerp(MN, fin);
+        fin -= MN.s;
+        const double ih01 = frcp_(x1 - x0), M01 = (y1 - cn) * ih01;
+        const double D1 = slope_interior(ih01, ih12, M01, M12);          // slope at old node q + 1
+        const int pn = f + k + 1 - o;
+        if (INT || (pn >= pa && pn < pb)) {
+          const double sx = Xj - x1, dx2_ = x2 - Xj;
+          ok &= (sx != 0.0) & (dx2_ != 0.0) & ((sx > 0.0) == (dx2_ > 0.0)) & ((sx > 0.0) != (blk != 0));
+          const double u = sx * ih12, dd = D1 + D2;
+          const double c3 = fma(-2.0, M12, dd), c2 = fma(3.0, M12, -dd) - D1;
+          *pc = fma(sx, fma(u, fma(u, c3, c2), D1), y1);
+          if (do_hash) hstep += idx_term(it_, blk, blk ? (nn - 1 - pn) : pn, blk ? (no - 2 - (pn + o)) : (pn + o), 3);
+        }
+        x2 = x1; x1 = x0; y1 = cn; ih12 = ih01; M12 = M01; D2 = D1;
+      };
+      const int kI_hi = mcl - 5;                             // with mcl <= len: not among the last four rows, pn < pb
       if (tid == 0) for (int b = 0; b < STG_NBB - 1 && b < nbatch_b; ++b) issue_b(b);
       for (int b = 0; b < nbatch_b; ++b) {
         const int buf = b % STG_NBB;
@@ -625,30 +669,15 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
         mbar_wait(&fullb[buf], (stg_par >> buf) & 1u);
         stg_par ^= 1u << buf;
         const int hi = m - 2 - b * STG_R, lo = max(hi - STG_R + 1, 0);
-        const double *rs_ = stg + (size_t)buf * (3 * STG_R * T) + tid, *as_ = rs_ + STG_R * T, *gs_ = as_ + STG_R * T;
+        const double *const rp0 = stg + (size_t)buf * (3 * STG_R * T) + tid;            // row lo
+        double *const pc0 = Cn + (size_t)(lo + 1 - o) * T + tid;                         // new node of row lo
+        if (hi - lo + 1 == STG_R && lo >= 4 && hi <= kI_hi) {
+#pragma unroll
+          for (int q = STG_R - 1; q >= 0; --q) frow(std::true_type{}, lo + q, rp0 + q * (3 * T), pc0 + q * T);
+        } else {
 #pragma unroll 1
-        for (int k = hi; k >= lo; --k) {
-          if (k <= len - 2) {
-            const int oo = (k - lo) * T;
-            cn = rs_[oo] - as_[oo] * spv - gs_[oo] * cn;     // solved value of old node q = f + k
-            if (k < 4) sh[k][tid] = cn;
-            if (k >= len - 4) sh[4 + (k - (len - 4))][tid] = cn;
-            const double x0 = s2_lerp(MO, fio);
-            fio -= MO.s;
-            const double ih01 = frcp_(x1 - x0), M01 = (y1 - cn) * ih01;
-            const double D1 = slope_interior(ih01, ih12, M01, M12);      // slope at old node q + 1
-            const int pn = f + k + 1 - o;                    // the new node of old interval [q + 1, q + 2]
-            if (pn >= pa && pn < pb) {
-              const double Xj = s2_at(MN, pn);
-              const double sx = Xj - x1, dx2_ = x2 - Xj;
-              ok &= (sx != 0.0) & (dx2_ != 0.0) & ((sx > 0.0) == (dx2_ > 0.0)) & ((sx > 0.0) != (blk != 0));
-              const double u = sx * ih12, dd = D1 + D2;
-              const double c3 = fma(-2.0, M12, dd), c2 = fma(3.0, M12, -dd) - D1;
-              Cn[(size_t)(pn - f) * T + tid] = fma(sx, fma(u, fma(u, c3, c2), D1), y1);
-              if (do_hash) hstep += idx_term(it_, blk, blk ? (nn - 1 - pn) : pn, blk ? (no - 2 - (pn + o)) : (pn + o), 3);
-            }
-            x2 = x1; x1 = x0; y1 = cn; ih12 = ih01; M12 = M01; D2 = D1;
-          }
+          for (int k = hi; k >= lo; --k)
+            if (k <= len - 2) frow(std::false_type{}, k, rp0 + (k - lo) * (3 * T), pc0 + (k - lo) * T);
         }
         __syncthreads();
       }
@@ -702,12 +731,12 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
           mbar_wait(&fullb[buf], (stg_par >> buf) & 1u);
           stg_par ^= 1u << buf;
           const int hi = m - 2 - b * STG_R, lo = max(hi - STG_R + 1, 0);
-          const double *rs_ = stg + (size_t)buf * (3 * STG_R * T) + tid, *as_ = rs_ + STG_R * T, *gs_ = as_ + STG_R * T;
+          const double *const rp0 = stg + (size_t)buf * (3 * STG_R * T) + tid;
 #pragma unroll 1
           for (int k = hi; k >= lo; --k) {
             if (k <= len - 2) {
-              const int oo = (k - lo) * T;
-              cn = rs_[oo] - as_[oo] * spv - gs_[oo] * cn;
+              const double *rp = rp0 + (k - lo) * (3 * T);
+              cn = rp[0] - rp[T] * spv - rp[2 * T] * cn;
               C[(size_t)k * T + tid] = cn;
             }
           }
