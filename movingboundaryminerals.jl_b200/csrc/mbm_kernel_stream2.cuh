@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
     S.newton_R = A.newton_R ? A.newton_R[mem] : 0.0;
     bool mine = A.only_deferred ? (S.status == -1) : (S.status == 0);
     const int mneed = (S.n1 + S.n2 + 2 + (T - 3)) / (T - 2);
-    const bool ok = (S.V != 0.0) && (S.MRefin == 1.0) && S.n1 >= 3 && S.n2 >= 3 && mneed <= MC &&
+    // moving interface: uniform regrid (MRefin == 1); fixed interface (V_ip == 0: no regrid, any mesh that is a LinRange pair)
+    const bool ok = ((S.V != 0.0 && S.MRefin == 1.0) || (S.V == 0.0 && A.dt_mode != DT_ADV)) && S.n1 >= 3 && S.n2 >= 3 && mneed <= MC &&
                     A.capL + 1 <= S2_MAX_D && A.capR + 1 <= S2_MAX_D;
     if (mine && !ok) { if (!A.only_deferred) A.status[mem] = -1; mine = false; }
     S.use_chain = mine ? 1 : 0;
@@ -332,6 +333,7 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
 
   unsigned long long hash_local = 0ull;
   const bool do_hash = (A.idx_hash != nullptr);
+  const bool fixedV = (S.V == 0.0);            // fixed interface: advect_interface_regrid! / regrid! leave the meshes (:57-61, :900-903)
   HistCache hc;
   if (tid == 0) hist_load(hc, P, S.hidx);
 
@@ -368,7 +370,8 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
         G.n[0] = n1; G.n[1] = n2;
         const double Rnew = xadd(S.Ri1, xmul(S.V, S.dt));                                        // functions.jl:31
         G.Rnew = Rnew;
-        if (S.V > 0.0) {
+        if (fixedV) { G.Rnew = S.Ri1; G.fast = 0; S.nr1 = n1; S.nr2 = n2; Lnew = Lcur; }         // both interface nodes ARE Ri1
+        else if (S.V > 0.0) {
           if (n1 + 1 > A.capL) rc = 10;
           else {
             S.Ri1 = Rnew;
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
         }
         G.n[0] = S.n1; G.n[1] = S.n2;
       }
-      if (!rc) {                                                                                  // regrid! :873-889
+      if (!rc && !fixedV) {                                                                       // regrid! :873-889
         long long nr1 = S.n1, nr2 = S.n2;
         if (S.V > 0.0) nr1 = (long long)rint(xmul(xmul(S.Ri1, xinv(xsub(S.Ri2, S.Ri1))), (double)nr2));
         else nr2 = (long long)rint(xmul(xmul(S.Ri2, xinv(xsub(S.Ri2, S.Ri1))), (double)nr1));
@@ -399,7 +402,7 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
         }
         if (rc) S.Fl = 2;
       }
-      if (!rc) {
+      if (!rc && !fixedV) {
         G.nr[0] = S.nr1; G.nr[1] = S.nr2;
         G.MN[0] = s2_mesh(0.0, S.Ri1, S.nr1, false);
         G.MN[1] = s2_mesh(S.Ri1, S.Ri2, S.nr2, true);
@@ -746,7 +749,7 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
       if (tid == 0) { C[paddr(T, L, 0, n1 - 1)] = aif; C[paddr(T, L, 1, n2 - 1)] = bif; }
       __threadfence_block();
       __syncthreads();
-      {
+      if (!fixedV) {
         const int nblk = (tid >= LN.colR0) ? 1 : 0;
         const int ncol = nblk ? (tid - LN.colR0) : tid;
         const int nn = nblk ? nr2 : nr1;
@@ -761,16 +764,18 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
           else pchip_run_stream2<T, false>(xo, xn, C, L, nblk, no, nn, Cn, idx0, cnt, 0, hash_local);
         }
       }
-      if (tid == 0) atomicAdd(&g_s2_twopass_steps, 1ull);
+      if (tid == 0) atomicAdd(&g_s2_twopass_steps, 1ull);          // (fixed-interface steps are counted here too)
     }
     __threadfence_block();
     __syncthreads();
-    { double *tp = C; C = Cn; Cn = tp; }
+    if (!fixedV) { double *tp = C; C = Cn; Cn = tp; }
     if (tid == 0) {
-      S.n1 = S.nr1; S.n2 = S.nr2;
-      Lcur = Lnew;
-      S.dx1 = xsub(linrange_at(0.0, S.Ri1, S.n1, S.n1 - 1), linrange_at(0.0, S.Ri1, S.n1, S.n1 - 2));   // regrid! :893-894
-      S.dx2 = xsub(linrange_at(S.Ri1, S.Ri2, S.n2, 1), linrange_at(S.Ri1, S.Ri2, S.n2, 0));
+      if (!fixedV) {
+        S.n1 = S.nr1; S.n2 = S.nr2;
+        Lcur = Lnew;
+        S.dx1 = xsub(linrange_at(0.0, S.Ri1, S.n1, S.n1 - 1), linrange_at(0.0, S.Ri1, S.n1, S.n1 - 2));   // regrid! :893-894
+        S.dx2 = xsub(linrange_at(S.Ri1, S.Ri2, S.n2, 1), linrange_at(S.Ri1, S.Ri2, S.n2, 0));
+      }
       S.steps += 1;
       const double cf = C[paddr(T, Lnew, 0, 0)], cl = C[paddr(T, Lnew, 1, 0)], ci = C[paddr(T, Lnew, 0, S.n1 - 1)];
       if (!isfinite(cf) || !isfinite(cl) || !isfinite(ci) || !isfinite(S.Ri1)) S.status = 11;

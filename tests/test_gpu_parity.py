@@ -544,3 +544,27 @@ def test_streaming_other_meshes_take_the_first_kernel(oracle, cuda_lib):
     assert eg.run(cuda_lib, max_steps=10, flags=abi.FLAG_FORCE_STREAMING) == 0
     assert _stream_pass_counts(cuda_lib) == (f0, t0)
     compare(eo, eg)
+
+
+@pytest.mark.parametrize("kind", ["mb", "flux"])
+def test_streaming_fixed_interface_uniform_mesh(oracle, cuda_lib, kind):
+    """config 5's fixed-mesh variant (V_ip = 0 on LinRange meshes): the closed-form streaming kernel without the regrid -
+    forward sweep, back-substitution in place; against the oracle (no regrid: no checksum terms)"""
+    pars = []
+    for res, r in (([3000, 3000], 0.45), ([2500, 4000], 0.3), ([2600, 4001], 0.6)):
+        p = d.pars_MB_growth() if kind == "mb" else d.pars_DCGF()
+        p.update(V_ip=0.0, res=res, MRefin=1.0, Ri=[r, 1.0], t_tot=2e4, KD_ar=(0.1, 0.3), Cl_i=0.5, Cr_i=5.0)
+        if kind == "flux":
+            p.update(Di=[4e-7, 5e-8], T_ar=(1273.15, 923.15))
+        pars.append(p)
+    for n in (1, 2, 3):
+        for p in pars:
+            p.update(n=n)
+        eo, _ = d.build_couple_ensemble(pars, oracle, cap_left=4100, cap_right=4100)
+        eg, _ = d.build_couple_ensemble(pars, cuda_lib, cap_left=4100, cap_right=4100)
+        f0, t0 = _stream_pass_counts(cuda_lib)
+        assert eo.run(oracle, max_steps=50) == 0
+        assert eg.run(cuda_lib, max_steps=50, flags=abi.FLAG_FORCE_STREAMING) == 0
+        f1, t1 = _stream_pass_counts(cuda_lib)
+        assert (f1 - f0, t1 - t0) == (0, 150)
+        compare(eo, eg)

@@ -8,7 +8,10 @@ lib = mbm_b200.load_cuda_library()
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 res = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
-ens, _ = d.build_couple_ensemble(E.c5_highres(M, res, max_steps=100), lib, cap_left=res + 4, cap_right=res + 4)
+pars = E.c5_highres(M, res, max_steps=100)
+if os.environ.get('V0'):                      # config 5's fixed-mesh variant: V_ip = 0
+    for p in pars: p.update(V_ip=0.0)
+ens, _ = d.build_couple_ensemble(pars, lib, cap_left=res + 4, cap_right=res + 4)
 if os.environ.get('NOHASH'): ens.arrays['idx_hash'] = None
 ens.run(lib, max_steps=2)
 n0 = int(ens.node_steps.sum())
