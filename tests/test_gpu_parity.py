@@ -568,3 +568,35 @@ def test_streaming_fixed_interface_uniform_mesh(oracle, cuda_lib, kind):
         f1, t1 = _stream_pass_counts(cuda_lib)
         assert (f1 - f0, t1 - t0) == (0, 150)
         compare(eo, eg)
+
+
+def test_streaming_closed_form_failure_states(oracle, cuda_lib):
+    """members that stop inside a step on the closed-form streaming path: interface too fast in either direction
+    (functions.jl:39 / :52), capacity exceeded by regrid!'s node counts, history too short (status 6) - same status, step
+    count, t, dt and Ri as the oracle (the reference throws there, so the arrays of a failed member are not defined; the
+    member that fails before the advection keeps its last completed state, which is compared), beside members that run on"""
+    def mk(**kw):
+        p = d.pars_MB_growth()
+        p.update(res=[2000, 2000], MRefin=1.0, Ri=[0.45, 1.0], t_tot=2e4, KD_ar=(0.1, 0.1), Cl_i=0.5, Cr_i=5.0, V_ip=1e-7)
+        p.update(**kw)
+        return p
+    pars = [mk(), mk(CFL=8.0, V_ip=-1e-4, t_tot=50.0), mk(CFL=8.0, V_ip=1e-4, t_tot=50.0), mk(V_ip=-1e-7), mk(V_ip=2e-7)]
+    # capacities: the resorption member's nr[2] wants 2000 / 0.55 = 3636 nodes at its first regrid
+    eo, _ = d.build_couple_ensemble(pars, oracle, cap_left=2100, cap_right=2600)
+    eg, _ = d.build_couple_ensemble(pars, cuda_lib, cap_left=2100, cap_right=2600)
+    for e in (eo, eg):                                  # member 4: its history ends after a few steps
+        for k in ("t_ar", "T_ar", "KD_ar"):
+            e.arrays[k] = np.repeat(e.arrays[k], 5, axis=0) if e.arrays[k].shape[0] == 1 else e.arrays[k]
+        e.arrays["t_ar"][4] = np.linspace(0.0, 25.0 * float(eo.arrays["t_ar"][0, -1]) / 9352.0 / 10.0, e.hist_len)
+    assert eo.run(oracle, max_steps=40) == 0
+    assert eg.run(cuda_lib, max_steps=40, flags=abi.FLAG_FORCE_STREAMING) == 0
+    assert list(eo.status) == list(eg.status), (eo.status, eg.status)
+    assert list(eo.status) == [0, 2, 1, 10, 6], eo.status
+    assert np.array_equal(eo.arrays["it"], eg.arrays["it"])
+    assert np.array_equal(eo.Ri, eg.Ri) and np.array_equal(eo.t, eg.t) and np.array_equal(eo.dt, eg.dt)
+    for m in (0, 4):
+        assert np.array_equal(eo.res[m], eg.res[m]) and eo.arrays["idx_hash"][m] == eg.arrays["idx_hash"][m]
+        n1, n2 = (int(v) for v in eo.res[m])
+        assert np.array_equal(eo.x_left[m, :n1], eg.x_left[m, :n1]), m
+        assert np.array_equal(eo.x_right[m, :n2], eg.x_right[m, :n2]), m
+        assert _relerr(eo.C_left[m, :n1], eg.C_left[m, :n1]) < TOL and _relerr(eo.C_right[m, :n2], eg.C_right[m, :n2]) < TOL, m
