@@ -32,6 +32,12 @@ namespace mbm {
 constexpr int S2_MAX_D = 300000;          // largest LinRange divisor the corrected reciprocal division is checked for
 constexpr int S2_MIN_ROWS = 16;           // shortest column the fused pass takes
 constexpr int S2_MAX_FIX = 10;            // most deferred nodes per column the fused pass accepts
+// Fill-in cutoff.  The fill-in column A_k of a chunk (its rows' dependence on the previous separator) decays geometrically
+// along the chunk (|A_k| = |sub inv| |A_k-1|, FEM rows are strictly diagonally dominant): after ~40..170 of a column's
+// ~500 rows A_k s_prev is below the last bit of C_k.  Rows from Kc on (a multiple of the batch length, per member and
+// step) are therefore stored as (R, G) pairs: every |A_k| dropped is checked against S2_A_DROP in the sweep itself (a
+// violation repeats the sweep without cutoff), Kc of the next step comes from where the columns fell below S2_A_ZERO.
+constexpr double S2_A_DROP = 1e-19, S2_A_ZERO = 1e-21;
 
 // diagnostics (tests): steps taken by the fused pass / by the two-pass path since the library was loaded
 __device__ unsigned long long g_s2_fused_steps = 0ull, g_s2_twopass_steps = 0ull;
@@ -224,6 +230,7 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
                *const exR = sh[5], *const red0 = sh[8], *const red1 = sh[9];
   __shared__ StreamLayout Lcur, Lnew;
   __shared__ Geo2 G;
+  __shared__ int s2_kz, s2_Kc;                 // fill-in cutoff: where this step's columns fell below S2_A_ZERO / cutoff row in use
   extern __shared__ __align__(128) double stg[];
   __shared__ __align__(8) unsigned long long fullb[STG_NBF];
   unsigned stg_par = 0;
@@ -333,6 +340,7 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
 
   unsigned long long hash_local = 0ull;
   const bool do_hash = (A.idx_hash != nullptr);
+  if (tid == 0) { s2_Kc = 0x3fffffff; s2_kz = 0; }        // first step: no cutoff (Kc is read after the scalar phase's barrier)
   const bool fixedV = (S.V == 0.0);            // fixed interface: advect_interface_regrid! / regrid! leave the meshes (:57-61, :900-903)
   HistCache hc;
   if (tid == 0) hist_load(hc, P, S.hidx);
@@ -466,7 +474,16 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
     }
     fence_proxy_async();
     __syncthreads();
-    {
+    // rows k < Kc: (R, A, G) at 3 k T; rows k >= Kc: (R, G) at 3 Kc T + 2 (k - Kc) T
+    int Kc = s2_Kc;
+#ifdef MBM_S2_NO_CUTOFF
+    Kc = 0x3fffffff;
+#endif
+    auto row_ptr = [&](const int k) { return RAG + ((k < Kc) ? (size_t)k * (3 * T) : (size_t)Kc * (3 * T) + (size_t)(k - Kc) * (2 * T)) + tid; };
+    for (int attempt = 0;; ++attempt) {
+      Ap = 0.0; Gp = 0.0; Rp = 0.0; P0 = 0.0; Qa = 0.0; Qc = 0.0;
+      int kz = 0x3fffffff;                     // first row of this column whose fill-in is below S2_A_ZERO
+      bool viol = false;                       // a fill-in value above S2_A_DROP was not stored
       // forward sweep: as in the first streaming kernel, x of every row from the closed form (fi: node index of the
       // NEXT row's node in its LinRange, stepped exactly by +-1)
       const int sd = blk ? -1 : 1;
@@ -484,8 +501,8 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
       bA = 0.0; bR = 0.0;
       // one row of the sweep (k: row of the column), given the next node's x and C; rows go to pr[0] (R), pr[T] (A), pr[2T] (G).
       // INTERIOR rows (neither the first nor the last row of the column) carry no tests of k.
-      auto fwd_row = [&](auto interior, const int k, double *pr, const double x_next, const double c_next) {
-        constexpr bool INT = decltype(interior)::value;
+      auto fwd_row = [&](auto interior, auto with_a, const int k, double *pr, const double x_next, const double c_next) {
+        constexpr bool INT = decltype(interior)::value, HASA = decltype(with_a)::value;
         const bool first = INT ? false : (k == 0), last = INT ? false : (k == len - 1);
         double Aself, A12, Anext, kk;
         elem_mats_dir<NDIM>(x_self, x_next, Dsd, idts, Aself, A12, Anext, kk);
@@ -498,7 +515,8 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
         const double An = first ? (sub * inv) : (-sub * Ap * inv);
         const double Gn = sup * inv;
         const double Rn = (rhs - sub * Rp) * inv;
-        pr[0] = Rn; pr[T] = An; pr[2 * T] = Gn;
+        if (HASA) { pr[0] = Rn; pr[T] = An; pr[2 * T] = Gn; if (fabs(An) < S2_A_ZERO) kz = min(kz, k); }
+        else { pr[0] = Rn; pr[T] = Gn; viol |= !(fabs(An) < S2_A_DROP); }
         if (!last) { bR = fma(pi, Rn, bR); bA = fma(pi, An, bA); pi = -pi * Gn; }
         if (mb) {
           const double Vn = powd<NDIM>(x_next);
@@ -528,14 +546,24 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
           stg_par ^= 1u << buf;
           const double *cs_ = stg + (size_t)buf * (STG_R * T) + tid;
           const int k0 = b * STG_R, nr = min(STG_R, nrows - k0);
-          double *const pr0 = RAG + (size_t)k0 * (3 * T) + tid;
+          const bool hasA = (k0 < Kc);                       // Kc is a multiple of the batch length: whole batches
+          double *const pr0 = row_ptr(k0);
           if (nr == STG_R && k0 >= 1 && k0 + STG_R <= len - 1) {
             // a batch of interior rows: straight-line code, immediate offsets
+            if (hasA) {
 #pragma unroll
-            for (int rr = 0; rr < STG_R; ++rr) {
-              const double xn_ = s2_lerp(MO, fi);
-              fi += MO.s;
-              fwd_row(std::true_type{}, k0 + rr, pr0 + rr * (3 * T), xn_, cs_[rr * T]);
+              for (int rr = 0; rr < STG_R; ++rr) {
+                const double xn_ = s2_lerp(MO, fi);
+                fi += MO.s;
+                fwd_row(std::true_type{}, std::true_type{}, k0 + rr, pr0 + rr * (3 * T), xn_, cs_[rr * T]);
+              }
+            } else {
+#pragma unroll
+              for (int rr = 0; rr < STG_R; ++rr) {
+                const double xn_ = s2_lerp(MO, fi);
+                fi += MO.s;
+                fwd_row(std::true_type{}, std::false_type{}, k0 + rr, pr0 + rr * (2 * T), xn_, cs_[rr * T]);
+              }
             }
           } else {
 #pragma unroll 1
@@ -545,15 +573,30 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
                 const bool last = (k == len - 1);
                 const double xn_ = s2_lerp(MO, fi);
                 fi += MO.s;
-                fwd_row(std::false_type{}, k, pr0 + rr * (3 * T), last ? x_halo_next : xn_, last ? c_halo_next : cs_[rr * T]);
+                if (hasA) fwd_row(std::false_type{}, std::true_type{}, k, pr0 + rr * (3 * T), last ? x_halo_next : xn_, last ? c_halo_next : cs_[rr * T]);
+                else fwd_row(std::false_type{}, std::false_type{}, k, pr0 + rr * (2 * T), last ? x_halo_next : xn_, last ? c_halo_next : cs_[rr * T]);
               }
             }
           }
           __syncthreads();
         }
-        if (len == m) fwd_row(std::false_type{}, m - 1, RAG + (size_t)(m - 1) * (3 * T) + tid, x_halo_next, c_halo_next);
+        if (len == m) {
+          if (m - 1 < Kc) fwd_row(std::false_type{}, std::true_type{}, m - 1, row_ptr(m - 1), x_halo_next, c_halo_next);
+          else fwd_row(std::false_type{}, std::false_type{}, m - 1, row_ptr(m - 1), x_halo_next, c_halo_next);
+        }
       }
       bG = -pi;
+      // cutoff bookkeeping: a dropped fill-in value that was not negligible repeats the sweep without cutoff (the state C is
+      // untouched by the sweep); otherwise the cutoff of the next step follows where this step's columns became negligible
+      if (__syncthreads_or(viol ? 1 : 0)) {
+        Kc = 0x3fffffff;
+        if (tid == 0) s2_Kc = Kc;
+        continue;
+      }
+      kz = min(kz, len);                       // columns shorter than their cutoff do not count
+      for (int o_ = 16; o_ > 0; o_ >>= 1) kz = max(kz, __shfl_xor_sync(0xffffffffu, kz, o_));
+      if (lane == 0) atomicMax(&s2_kz, kz);
+      break;
     }
     fence_proxy_async();
     exA[tid] = bA; exG[tid] = bG; exR[tid] = bR;
@@ -604,14 +647,15 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
     const double beta = blk ? bif : aif;
     const double sj = active ? (red0[tid] + red1[tid] * beta) : 0.0;
     const double spv = (active && jc > 0) ? (red0[tid - 1] + red1[tid - 1] * beta) : 0.0;
-    // rows m-2 .. 0 of (R, A, G) staged through shared memory in batches of STG_R rows (descending): both variants of
-    // the second pass read them this way
+    // rows m-2 .. 0 of the elimination staged through shared memory, batch j = rows [j R, j R + R - 1] (the boundaries of
+    // the forward sweep's batches, so a batch lies on one side of the cutoff), taken from the top batch down: the b-th
+    // batch issued / consumed is j = nbatch_b - 1 - b.  Both variants of the second pass read the rows this way.
     const int nrows_b = m - 1, nbatch_b = (nrows_b + STG_R - 1) / STG_R;
     auto issue_b = [&](const int b) {
-      const int hi = m - 2 - b * STG_R, lo = max(hi - STG_R + 1, 0), nr = hi - lo + 1, buf = b % STG_NBB;
-      const unsigned bytes = (unsigned)nr * 3u * T * 8u;
+      const int j = nbatch_b - 1 - b, lo = j * STG_R, hi = min(lo + STG_R - 1, m - 2), nr = hi - lo + 1, buf = b % STG_NBB;
+      const unsigned bytes = (unsigned)nr * ((lo < Kc) ? 3u : 2u) * T * 8u;
       mbar_expect_tx(&fullb[buf], bytes);
-      bulk_g2s(stg + (size_t)buf * (3 * STG_R * T), RAG + (size_t)lo * (3 * T), bytes, &fullb[buf]);
+      bulk_g2s(stg + (size_t)buf * (3 * STG_R * T), row_ptr(lo) - tid, bytes, &fullb[buf]);
     };
 
     bool fused_done = false;
@@ -640,9 +684,10 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
       // one row (k) of the walk: back-substitute old node q = f + k, complete the stencil of old interval [q + 1, q + 2]
       // and evaluate its new node pn = q + 1 - o into *pc.  rp: the row's (R, A, G) in the staging buffer.  INTERIOR rows
       // (4 <= k <= kI_hi) publish nothing and always evaluate.
-      auto frow = [&](auto interior, const int k, const double *rp, double *pc) {
-        constexpr bool INT = decltype(interior)::value;
-        cn = rp[0] - rp[T] * spv - rp[2 * T] * cn;           // solved value of old node q
+      auto frow = [&](auto interior, auto with_a, const int k, const double *rp, double *pc) {
+        constexpr bool INT = decltype(interior)::value, HASA = decltype(with_a)::value;
+        if (HASA) cn = rp[0] - rp[T] * spv - rp[2 * T] * cn;  // solved value of old node q
+        else cn = rp[0] - rp[T] * cn;                         // (beyond the cutoff: (R, G) rows)
         if (!INT) {
           if (k < 4) sh[k][tid] = cn;
           if (k >= len - 4) sh[4 + (k - (len - 4))][tid] = cn;
@@ -671,16 +716,25 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
         if (tid == 0 && b + STG_NBB - 1 < nbatch_b) issue_b(b + STG_NBB - 1);
         mbar_wait(&fullb[buf], (stg_par >> buf) & 1u);
         stg_par ^= 1u << buf;
-        const int hi = m - 2 - b * STG_R, lo = max(hi - STG_R + 1, 0);
+        const int lo = (nbatch_b - 1 - b) * STG_R, hi = min(lo + STG_R - 1, m - 2);
         const double *const rp0 = stg + (size_t)buf * (3 * STG_R * T) + tid;            // row lo
         double *const pc0 = Cn + (size_t)(lo + 1 - o) * T + tid;                         // new node of row lo
+        const bool hasA = (lo < Kc);
         if (hi - lo + 1 == STG_R && lo >= 4 && hi <= kI_hi) {
+          if (hasA) {
 #pragma unroll
-          for (int q = STG_R - 1; q >= 0; --q) frow(std::true_type{}, lo + q, rp0 + q * (3 * T), pc0 + q * T);
+            for (int q = STG_R - 1; q >= 0; --q) frow(std::true_type{}, std::true_type{}, lo + q, rp0 + q * (3 * T), pc0 + q * T);
+          } else {
+#pragma unroll
+            for (int q = STG_R - 1; q >= 0; --q) frow(std::true_type{}, std::false_type{}, lo + q, rp0 + q * (2 * T), pc0 + q * T);
+          }
         } else {
 #pragma unroll 1
           for (int k = hi; k >= lo; --k)
-            if (k <= len - 2) frow(std::false_type{}, k, rp0 + (k - lo) * (3 * T), pc0 + (k - lo) * T);
+            if (k <= len - 2) {
+              if (hasA) frow(std::false_type{}, std::true_type{}, k, rp0 + (k - lo) * (3 * T), pc0 + (k - lo) * T);
+              else frow(std::false_type{}, std::false_type{}, k, rp0 + (k - lo) * (2 * T), pc0 + (k - lo) * T);
+            }
         }
         __syncthreads();
       }
@@ -733,13 +787,14 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
           if (tid == 0 && b + STG_NBB - 1 < nbatch_b) issue_b(b + STG_NBB - 1);
           mbar_wait(&fullb[buf], (stg_par >> buf) & 1u);
           stg_par ^= 1u << buf;
-          const int hi = m - 2 - b * STG_R, lo = max(hi - STG_R + 1, 0);
+          const int lo = (nbatch_b - 1 - b) * STG_R, hi = min(lo + STG_R - 1, m - 2);
           const double *const rp0 = stg + (size_t)buf * (3 * STG_R * T) + tid;
+          const bool hasA = (lo < Kc);
 #pragma unroll 1
           for (int k = hi; k >= lo; --k) {
             if (k <= len - 2) {
-              const double *rp = rp0 + (k - lo) * (3 * T);
-              cn = rp[0] - rp[T] * spv - rp[2 * T] * cn;
+              const double *rp = rp0 + (k - lo) * (hasA ? 3 * T : 2 * T);
+              cn = hasA ? (rp[0] - rp[T] * spv - rp[2 * T] * cn) : (rp[0] - rp[T] * cn);
               C[(size_t)k * T + tid] = cn;
             }
           }
@@ -770,6 +825,11 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
     __syncthreads();
     if (!fixedV) { double *tp = C; C = Cn; Cn = tp; }
     if (tid == 0) {
+      {                                            // cutoff of the next step: past the last column that was still above zero
+        int kc = ((s2_kz + 8 + STG_R - 1) / STG_R) * STG_R;
+        if (kc + STG_R >= m - 1) kc = 0x3fffffff;
+        s2_Kc = kc; s2_kz = 0;
+      }
       if (!fixedV) {
         S.n1 = S.nr1; S.n2 = S.nr2;
         Lcur = Lnew;
