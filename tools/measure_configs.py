@@ -75,6 +75,15 @@ def main():
                        lambda M: E.c5_highres(M, 65536, max_steps=100),
                        lambda lib, P: d.build_couple_ensemble(P, lib, cap_left=65540, cap_right=65540)[0],
                        296, 20, 1, tol=1e-9))
+    if "c5" in which or "c5v0" in which:
+        def c5v0(M):
+            pars = E.c5_highres(M, 65536, max_steps=100)
+            for p in pars:
+                p.update(V_ip=0.0)
+            return pars
+        res.append(run("c5 fixed-mesh variant: V_ip = 0, n=65536/phase, LinRange meshes (closed-form streaming kernel, no regrid)",
+                       c5v0, lambda lib, P: d.build_couple_ensemble(P, lib, cap_left=65540, cap_right=65540)[0],
+                       296, 20, 1, tol=1e-9, ints=False))
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "configs.json").write_text(json.dumps(res, indent=1))
 
