@@ -600,3 +600,73 @@ def test_streaming_closed_form_failure_states(oracle, cuda_lib):
         assert np.array_equal(eo.x_left[m, :n1], eg.x_left[m, :n1]), m
         assert np.array_equal(eo.x_right[m, :n2], eg.x_right[m, :n2]), m
         assert _relerr(eo.C_left[m, :n1], eg.C_left[m, :n1]) < TOL and _relerr(eo.C_right[m, :n2], eg.C_right[m, :n2]) < TOL, m
+
+
+def test_full_size_properties_c4(oracle, cuda_lib):
+    """BASELINE.json configs[3] at its full member size (n = 1024 per phase, growth and resorption members), 300 members x
+    400 steps, through size-independent properties: every member valid; the closed system keeps its mass (the mass-balance
+    row, functions.jl:1094-1109: |Mass - Mass0| / Mass0, the reference's calc_mass_err, below 1e-9); a call cut into three
+    resumed calls returns the same bits; the interface moved by exactly sum(V dt); and two members against the oracle"""
+    from mbm_b200 import ensembles as E
+    pars = E.c4_mb_growth_resorption(300, res=1024, max_steps=10_000)
+    e1, _ = d.build_couple_ensemble(pars, cuda_lib, cap_left=2048, cap_right=2560)
+    e2 = e1.copy()
+    Ri0 = e1.Ri.copy()
+    assert e1.run(cuda_lib, max_steps=400, flags=abi.FLAG_MASS_FINAL) == 0
+    assert np.all(e1.status == 0) and np.all(e1.it == 400)
+    assert np.max(np.abs(e1.Mass - e1.Mass0) / e1.Mass0) < 1e-9
+    for steps in (150, 150, 100):
+        assert e2.run(cuda_lib, max_steps=steps, flags=abi.FLAG_MASS_FINAL) == 0
+    for k in ("res", "it", "Ri", "t", "dt", "idx_hash", "Mass", "node_steps"):
+        assert np.array_equal(e1.arrays[k], e2.arrays[k]), k
+    for m in range(e1.M):                                # (beyond res[m] the arrays keep whatever an earlier call stored)
+        for a, b in zip(e1.member(m), e2.member(m)):
+            assert np.array_equal(a, b), m
+    V = np.array([p["V_ip"] for p in pars])
+    grew = (e1.Ri[:, 0] - Ri0[:, 0]) * np.sign(V)
+    assert np.all(grew > 0) and np.all(e1.Ri[:, 1] == Ri0[:, 1])
+    # the solve sees one inserted node per step: between N + 1 and the final N + 1 nodes per step
+    assert np.all(e1.node_steps >= 400 * 2049)
+    eo, _ = d.build_couple_ensemble(pars[:2], oracle, cap_left=2048, cap_right=2560)
+    assert eo.run(oracle, max_steps=400, flags=abi.FLAG_MASS_FINAL) == 0
+    for m in range(2):
+        assert np.array_equal(eo.res[m], e1.res[m]) and eo.arrays["idx_hash"][m] == e1.arrays["idx_hash"][m]
+        for a, b in zip(eo.member(m), e1.member(m)):
+            assert _relerr(a, b) < TOL
+
+
+def test_full_size_properties_c5(oracle, cuda_lib):
+    """BASELINE.json configs[4] at its full member size (n = 65 536 per phase, MRefin = 1), 6 members x 12 steps on the
+    closed-form streaming kernel: fused pass on every step, mass kept, split calls return the same bits, meshes are
+    exactly the LinRanges of the final interface position, one member against the oracle (tolerance 1e-9: the two
+    elimination orders differ by ~5e-10 at 131 072 unknowns, profiles/README.md)"""
+    from mbm_b200 import ensembles as E
+    res = 65536
+    pars = E.c5_highres(6, res, max_steps=100)
+    e1, _ = d.build_couple_ensemble(pars, cuda_lib, cap_left=res + 4, cap_right=res + 4)
+    e2 = e1.copy()
+    f0, t0 = _stream_pass_counts(cuda_lib)
+    assert e1.run(cuda_lib, max_steps=12, flags=abi.FLAG_MASS_FINAL) == 0
+    f1, t1 = _stream_pass_counts(cuda_lib)
+    assert (f1 - f0, t1 - t0) == (72, 0)
+    assert np.all(e1.status == 0) and np.all(e1.it == 12) and np.all(e1.res == res)
+    assert np.max(np.abs(e1.Mass - e1.Mass0) / e1.Mass0) < 1e-9
+    for steps in (5, 7):
+        assert e2.run(cuda_lib, max_steps=steps, flags=abi.FLAG_MASS_FINAL) == 0
+    for k in ("x_left", "C_left", "x_right", "C_right", "res", "it", "Ri", "t", "dt", "idx_hash", "Mass", "node_steps"):
+        assert np.array_equal(e1.arrays[k], e2.arrays[k]), k
+    for m in range(6):
+        assert np.array_equal(e1.x_left[m, :res], _linrange(0.0, e1.Ri[m, 0], res))
+        assert np.array_equal(e1.x_right[m, :res], _linrange(e1.Ri[m, 0], e1.Ri[m, 1], res))
+    eo, _ = d.build_couple_ensemble(pars[:1], oracle, cap_left=res + 4, cap_right=res + 4)
+    assert eo.run(oracle, max_steps=12, flags=abi.FLAG_MASS_FINAL) == 0
+    assert np.array_equal(eo.res[0], e1.res[0]) and eo.arrays["idx_hash"][0] == e1.arrays["idx_hash"][0]
+    assert np.array_equal(eo.x_left[0], e1.x_left[0]) and np.array_equal(eo.x_right[0], e1.x_right[0])
+    for a, b in zip(eo.member(0), e1.member(0)):
+        assert _relerr(a, b) < 1e-9
+
+
+def _linrange(a, b, n):
+    """Julia's LinRange(a, b, n) (Base.lerpi): t = i / (n - 1), (1 - t) * a + t * b, every operation rounded once"""
+    t = np.arange(n, dtype=np.float64) / np.float64(n - 1)
+    return (1.0 - t) * a + t * b
