@@ -365,8 +365,10 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
     if (!A.workspace) return st->rc ? st->rc : MBM_RC_OOM;
   }
   // streaming kernel (long profiles on uniform meshes): chunk-interleaved workspace of 6 arrays x MC rows x 256 columns
+  // (the streaming kernels keep no per-step history: MBM_FLAG_RECORD calls stay with the general kernel, which does)
+  const bool wants_history = (flags & MBM_FLAG_RECORD) && A.rec != nullptr && A.rec_cap > 0;
   const bool use_stream = use_global && (A.inner_bc == MBM_BC_FLUX || A.inner_bc == MBM_BC_MB) && !getenv("MBM_NO_STREAM") &&
-                          A.ndim >= 1 && A.ndim <= 3;
+                          A.ndim >= 1 && A.ndim <= 3 && !wants_history;
   mbm::KArgs AS = A;
   if (use_stream) {
     const int MC = (A.capL + A.capR + 2 + 253) / 254 + 1;

@@ -670,3 +670,19 @@ def _linrange(a, b, n):
     """Julia's LinRange(a, b, n) (Base.lerpi): t = i / (n - 1), (1 - t) * a + t * b, every operation rounded once"""
     t = np.arange(n, dtype=np.float64) / np.float64(n - 1)
     return (1.0 - t) * a + t * b
+
+
+def test_step_history_on_the_global_memory_path(oracle, cuda_lib):
+    """MBM_FLAG_RECORD with members that do not fit shared memory (forced here): the streaming kernels keep no per-step
+    history, so the call stays with the general kernel - the `Mass` vector DCGF returns (Diff_couple_1D_general_Flux.jl:137)
+    must not be silently dropped"""
+    p = d.pars_MB_growth(); p.update(res=[300, 400], MRefin=1.0, KD_ar=(0.9, 0.6))
+    eo, _ = d.build_couple_ensemble([p], oracle, cap_left=700, cap_right=900)
+    eg, _ = d.build_couple_ensemble([p], cuda_lib, cap_left=700, cap_right=900)
+    assert eo.run(oracle, max_steps=40, rec_cap=64) == 0
+    assert eg.run(cuda_lib, max_steps=40, rec_cap=64, flags=abi.FLAG_FORCE_STREAMING) == 0
+    ro, rg = eo.arrays["rec"][0, :40], eg.arrays["rec"][0, :40]
+    assert np.all(ro[:, 0] > 0)
+    for c in range(4):
+        assert _relerr(ro[:, c], rg[:, c]) < 1e-11, c
+    compare(eo, eg)
