@@ -12,6 +12,7 @@
 // both blocks sweep with increasing storage index and every access of the row loops is base + immediate.  Loop body: reference main_codes/Diff_couple_1D_general_Flux.jl:87-130 with
 // Fl_regrid == 0 (functions.jl:58-61), examples/Diff_couple_MB.jl:87-109, Diff_couple_no_interaction.jl:96-124.
 #pragma once
+#include <type_traits>
 #include "mbm_kernel_v2.cuh"
 
 namespace mbm {
@@ -26,8 +27,14 @@ template <int T, int NDIM>
 __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(const KArgs A, const int member0) {
   extern __shared__ double smem[];
   __shared__ Scal S;
-  __shared__ double redS[T], redD[T], redU[T], red0[T + 32], red1[T];   // red0: per-step right-hand side, skewed (red_ix)
+  __shared__ double redSD[2 * T], redU[T], red0[T + 32], red1[T];       // red0: per-step right-hand side, skewed (red_ix)
+  double *const redS = redSD, *const redD = redSD + T;
   __shared__ double exA[T], exG[T], exR[T];
+  // step-time views of arrays the factorisation only needs while it runs: redB (the neighbour chunk's part of each reduced
+  // right-hand side, skewed like red0) and the solved first / last row of every chunk, which the neighbours' next forward
+  // sweep reads as halos (the sweep then touches only its own rows of C: no barrier between the steps' reads and writes)
+  double *const redB = redSD, *const hFirst = redU, *const hLast = exR;
+  static_assert(2 * T >= T + 32, "redB (T + 32 skewed entries) must fit redS | redD");
   __shared__ double red1c[T];                // solution of the reduced system for the interface-unknown column (matrix-only)
   __shared__ double rfac[RFAC_N(T) * 32];    // matrix part of the reduced solve (reduced_factor), redone per factorisation
 
@@ -129,6 +136,7 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
   // per-chunk constants of the factorisation (registers)
   double cQa = 0.0, cQc = 0.0, cGp = 0.0, cAp = 0.0, cbA = 0.0, cbG = -1.0;
   double r_s = 0.0, r_u = 0.0, r_inv = 1.0, r_Gp = 0.0;     // reduced row: sub, sup, 1/diag, G of the chunk's last row
+  double gi_prev = 0.0;                                     // r_Gp * r_inv of the previous chunk (0: none / it is a last chunk)
   double dt_full = 0.0, dtD_l = -1.0, dtD_r = -1.0;         // thread 0: cached find_dt
   HistCache hc;
   if (tid == 0) hist_load(hc, P, S.hidx);
@@ -300,9 +308,16 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
       if (active) { redS[tid] = r_s; redD[tid] = 1.0; redU[tid] = lastChunk ? 0.0 : r_u; red0[tid] = 0.0; red1[tid] = lastChunk ? -r_Gp : 0.0; }
       else { redS[tid] = 0.0; redD[tid] = 1.0; redU[tid] = 0.0; red0[tid] = 0.0; red1[tid] = 0.0; }
       __syncthreads();
+      // (exA / exG are free from here on: exA carries each chunk's r_Gp * r_inv to its right-hand neighbour)
+      exA[tid] = (active && !lastChunk) ? r_Gp * r_inv : 0.0;
       if (tid < 32) { reduced_solve<T, 2>(redS, redD, redU, red0, red1); reduced_factor<T>(redS, redD, redU, rfac); }
       __syncthreads();
       red1c[tid] = red1[tid];
+      gi_prev = (tid > 0) ? exA[tid - 1] : 0.0;
+      __syncthreads();                         // redS | redD, redU, exR change roles: step-time arrays from here
+      if (active) { hFirst[tid] = C[s0]; hLast[tid] = C[s0 + len - 1]; }
+      redB[red_ix<T>(tid)] = 0.0;
+      __syncthreads();
       if (bc == BC_FLUX) {
         // the flux row's coefficients only change with the factorisation: al*U + (be + al*U1)*a + (ga + de*W1)*b + de*W = 0
         __syncthreads();
@@ -317,16 +332,45 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
     }
 
     // ---------------- right-hand side + forward substitution with the resident factors ----------------------------------
+    // Two block barriers per step (flux / hold; the mass-balance row adds its block sum): chunks exchange their end values
+    // through hFirst / hLast, so the sweep reads and writes only its own rows of C; the reduced right-hand side is
+    // assembled from two contributions (the chunk's own: red0, its right-hand neighbour's: redB) without a barrier between
+    // them.  Chunks of 3 / 5 / 7 full rows run straight-line code with the rows of the elimination in registers.
     const int p = n1 - 1, q = N - 1;         // interface nodes (the right one is the last element of the reversed block)
     const double a_old = C[p], b_old = C[q];
     double c_halo_prev = 0.0, c_halo_next = 0.0;
     if (active) {
-      if (f > 0) c_halo_prev = C[s0 - 1];
-      c_halo_next = C[s0 + len];
+      if (f > 0) c_halo_prev = hLast[tid - 1];
+      c_halo_next = lastChunk ? (blk ? b_old : a_old) : hFirst[tid + 1];
     }
-    __syncthreads();
+    const int rix = red_ix<T>(tid), rixm = red_ix<T>(tid > 0 ? tid - 1 : 0);
     double P0 = 0.0, Rp = 0.0, bR = 0.0;
-    if (active) {
+    double Rr[7];                             // rows of the elimination of a 3 / 5 / 7-row chunk
+    const int fastM = (active && len == m && (m == 3 || m == 5 || m == 7)) ? m : 0;
+    auto fwd_fast = [&](auto mtag) {
+      constexpr int M = decltype(mtag)::value;
+      double c[M + 2];
+      c[0] = c_halo_prev; c[M + 1] = c_halo_next;
+#pragma unroll
+      for (int k = 0; k < M; ++k) c[k + 1] = C[s0 + k];
+      double rp = 0.0;
+#pragma unroll
+      for (int k = 0; k < M; ++k) {
+        const int s = s0 + k;
+        rp = fma(ML[s], c[k], fma(MD[s], c[k + 1], fma(MU[s], c[k + 2], -FS[s] * rp)));
+        Rr[k] = rp;
+        if (mb) P0 = fma(TQ[s], rp, P0);
+      }
+      Rp = rp;
+      double b = Rr[M - 2];
+#pragma unroll
+      for (int k = M - 3; k >= 0; --k) b = Rr[k] - FG[s0 + k] * b;
+      bR = b;
+    };
+    if (fastM == 5) fwd_fast(std::integral_constant<int, 5>{});
+    else if (fastM == 3) fwd_fast(std::integral_constant<int, 3>{});
+    else if (fastM == 7) fwd_fast(std::integral_constant<int, 7>{});
+    else if (active) {
       double c_prev = c_halo_prev, c_self = C[s0];
       int s = s0;
       // (two copies of the loop: the mass-balance functional is only accumulated for inner_bc = mb, and a test of a
@@ -355,15 +399,14 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
 #pragma unroll 1
         for (int k = len - 3; k >= 0; --k) { --sb; bR = C[sb] - FG[sb] * bR; }
       }
-      exR[tid] = bR;
     }
+    // right-hand side of the reduced system, row t = (Rp_t - r_Gp_t bR_{t+1}) r_inv_t in two parts: red0[t] = Rp_t r_inv_t by
+    // chunk t, redB[t] = -(r_Gp r_inv)_{t-1} bR_t by chunk t for row t - 1; its matrix part was factorised with the step
+    // matrix (reduced_factor)
+    red0[rix] = active ? Rp * r_inv : 0.0;
+    redB[rix] = -gi_prev * bR;
     __syncthreads();
-    // right-hand side of the reduced system; its matrix part was factorised with the step matrix (reduced_factor)
-    const int rix = red_ix<T>(tid), rixm = red_ix<T>(tid > 0 ? tid - 1 : 0);
-    if (active) red0[rix] = lastChunk ? Rp : (Rp - r_Gp * exR[tid + 1]) * r_inv;
-    else red0[rix] = 0.0;
-    __syncthreads();
-    if (tid < 32) reduced_apply<T, true>(rfac, red0);
+    if (tid < 32) reduced_apply<T, true, true>(rfac, red0, redB);
     __syncthreads();
 
     // ---------------- interface condition (set_inner_bc_flux! / _mb! / Dirichlet hold) ----------------------------------
@@ -393,17 +436,31 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
       const double sj = red0[rix] + red1c[tid] * beta;
       const double sp = (jc > 0) ? (red0[rixm] + red1c[tid - 1] * beta) : 0.0;
       double cn = sj;
-      int sb = s0 + (len - 1);
-      C[sb] = cn;
+      auto back_fast = [&](auto mtag) {
+        constexpr int M = decltype(mtag)::value;
+        C[s0 + M - 1] = cn;
+#pragma unroll
+        for (int k = M - 2; k >= 0; --k) { cn = Rr[k] - FA[s0 + k] * sp - FG[s0 + k] * cn; C[s0 + k] = cn; }
+      };
+      if (fastM == 5) back_fast(std::integral_constant<int, 5>{});
+      else if (fastM == 3) back_fast(std::integral_constant<int, 3>{});
+      else if (fastM == 7) back_fast(std::integral_constant<int, 7>{});
+      else {
+        int sb = s0 + (len - 1);
+        C[sb] = cn;
 #pragma unroll 2
-      for (int k = len - 2; k >= 0; --k) { --sb; cn = C[sb] - FA[sb] * sp - FG[sb] * cn; C[sb] = cn; }
+        for (int k = len - 2; k >= 0; --k) { --sb; cn = C[sb] - FA[sb] * sp - FG[sb] * cn; C[sb] = cn; }
+      }
+      hLast[tid] = sj; hFirst[tid] = cn;
+      // finite check of the step (status 11) on the outer ends, by the chunks that own them
+      if (jc == 0 && !isfinite(cn)) S.status = 11;
     }
     if (tid == 0) {
       C[p] = aif; C[q] = bif;
+      if (!isfinite(aif)) S.status = 11;
       S.steps += 1;
     }
     __syncthreads();
-    if (tid == 0 && (!isfinite(C[0]) || !isfinite(C[rb]) || !isfinite(C[p]))) S.status = 11;     // outer ends, interface
     if ((A.flags & F_RECORD) && A.rec) {
       double v[4] = {0.0, 0.0, 0.0, 0.0};
       for (int i = tid; i < n1 - 1; i += T)
@@ -415,8 +472,8 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
         double *r = A.rec + ((size_t)mem * (size_t)A.rec_cap + (size_t)(S.it - 1)) * 4;
         r[0] = v[0] + v[1]; r[1] = S.T; r[2] = S.KD; r[3] = S.Ri1;
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
   __syncthreads();
   // ---------------- store member ----------------

@@ -799,16 +799,27 @@ __device__ __forceinline__ void reduced_factor(const double *rs, const double *r
     ps = ns; pu = nu;
   }
 }
-template <int T, bool SKEW = false>
-__device__ __forceinline__ void reduced_apply(const double *fac, double *r0) {
+// PLUS: the right-hand side of row g is r0[g] + rb[g + 1] (rb: what the next chunk contributes to each row; same indexing)
+template <int T, bool SKEW = false, bool PLUS = false>
+__device__ __forceinline__ void reduced_apply(const double *fac, double *r0, const double *rb = nullptr) {
   constexpr int RPL = T / 32;
   const int lane = threadIdx.x;
   const int g0 = (SKEW && RPL > 1) ? lane * (RPL + 1) : lane * RPL;       // SKEW: r0 indexed by red_ix<T>
   const double *f = fac + lane;
   double R0[RPL];
-  R0[0] = r0[g0] * f[1 * 32];
+  double in[RPL];
 #pragma unroll
-  for (int k = 1; k < RPL; ++k) R0[k] = (r0[g0 + k] - f[(2 * k) * 32] * R0[k - 1]) * f[(2 * k + 1) * 32];
+  for (int k = 0; k < RPL; ++k) {
+    in[k] = r0[g0 + k];
+    if (PLUS) {
+      // row g + 1: the next row of the lane's chunk, or the first row of the next lane's chunk (none behind row T - 1)
+      const int nx = (k < RPL - 1) ? (g0 + k + 1) : ((SKEW && RPL > 1) ? (lane + 1) * (RPL + 1) : (lane + 1) * RPL);
+      in[k] += (k < RPL - 1 || lane < 31) ? rb[nx] : 0.0;
+    }
+  }
+  R0[0] = in[0] * f[1 * 32];
+#pragma unroll
+  for (int k = 1; k < RPL; ++k) R0[k] = (in[k] - f[(2 * k) * 32] * R0[k - 1]) * f[(2 * k + 1) * 32];
   const double *fa = f + 2 * RPL * 32;                    // A[k], G[k] pairs
   double bR0 = 0.0;
   if (RPL > 1) {
