@@ -42,8 +42,10 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
   const int mem = member0 + blockIdx.x;
   if (mem >= A.M) return;
   const int SZ = A.kcapR;                    // capacity of this kernel's arrays (n1 + n2 <= SZ)
-  double *X = smem, *C = smem + SZ, *FA = smem + 2 * (size_t)SZ, *FG = smem + 3 * (size_t)SZ, *FS = smem + 4 * (size_t)SZ,
-         *ML = smem + 5 * (size_t)SZ, *MD = smem + 6 * (size_t)SZ, *MU = smem + 7 * (size_t)SZ, *TQ = smem + 8 * (size_t)SZ;
+  // x, C, then the seven per-row quantities of the factorisation interleaved row by row, CO[7 s + j] (j = 0..6: mass-matrix
+  // row times inv (ml, md, mu), sub * inv, G, fill-in A, mass-balance weight): one row pointer and immediate offsets for
+  // every load of the row loops; seven is odd, so chunks of an odd number of rows still start in distinct banks
+  double *const X = smem, *const C = smem + SZ, *const CO = smem + 2 * (size_t)SZ;
   const int bc = A.inner_bc;
   const bool mb = (bc == BC_MB);
   MemberPtrs P;
@@ -137,6 +139,8 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
   double cQa = 0.0, cQc = 0.0, cGp = 0.0, cAp = 0.0, cbA = 0.0, cbG = -1.0;
   double r_s = 0.0, r_u = 0.0, r_inv = 1.0, r_Gp = 0.0;     // reduced row: sub, sup, 1/diag, G of the chunk's last row
   double gi_prev = 0.0;                                     // r_Gp * r_inv of the previous chunk (0: none / it is a last chunk)
+  const double *const co0 = CO + 7 * (size_t)s0;            // this chunk's rows of the factorisation and of the profile
+  double *const c0p = C + s0;
   double dt_full = 0.0, dtD_l = -1.0, dtD_r = -1.0;         // thread 0: cached find_dt
   HistCache hc;
   if (tid == 0) hist_load(hc, P, S.hidx);
@@ -274,12 +278,12 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
           const double inv = frcp(diag - sub * Gp);
           const double An = (k == 0) ? (sub * inv) : (-sub * Ap * inv);
           const double Gn = sup * inv;
-          FA[s] = An; FG[s] = Gn; FS[s] = sub * inv; ML[s] = ml * inv; MD[s] = md * inv; MU[s] = mu * inv;
+          CO[7 * (s) + 5] = An; CO[7 * (s) + 4] = Gn; CO[7 * (s) + 3] = sub * inv; CO[7 * (s) + 0] = ml * inv; CO[7 * (s) + 1] = md * inv; CO[7 * (s) + 2] = mu * inv;
           if (mb) {
             const double Vn = powd<NDIM>(x_next);
             const double wgt = 0.5 * fabs(Vn - Vs) + 0.5 * fabs(Vs - Vm);
-            if (k < len - 1) { const double tq = Qb + wgt; TQ[s] = tq; Qa = fma(-tq, An, Qa); Qb = -tq * Gn; }
-            else { Qc = Qb + wgt; TQ[s] = 0.0; }
+            if (k < len - 1) { const double tq = Qb + wgt; CO[7 * (s) + 6] = tq; Qa = fma(-tq, An, Qa); Qb = -tq * Gn; }
+            else { Qc = Qb + wgt; CO[7 * (s) + 6] = 0.0; }
             Vm = Vs; Vs = Vn;
           }
           Ap = An; Gp = Gn;
@@ -290,9 +294,9 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
         cbA = 0.0; cbG = -1.0;
         if (len > 1) {
           int sb = s0 + (len - 2);
-          cbA = FA[sb]; cbG = FG[sb];
+          cbA = CO[7 * (sb) + 5]; cbG = CO[7 * (sb) + 4];
 #pragma unroll 1
-          for (int k = len - 3; k >= 0; --k) { --sb; const double Gk = FG[sb]; cbA = FA[sb] - Gk * cbA; cbG = -Gk * cbG; }
+          for (int k = len - 3; k >= 0; --k) { --sb; const double Gk = CO[7 * (sb) + 4]; cbA = CO[7 * (sb) + 5] - Gk * cbA; cbG = -Gk * cbG; }
         }
         exA[tid] = cbA; exG[tid] = cbG;
       }
@@ -352,19 +356,18 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
       double c[M + 2];
       c[0] = c_halo_prev; c[M + 1] = c_halo_next;
 #pragma unroll
-      for (int k = 0; k < M; ++k) c[k + 1] = C[s0 + k];
+      for (int k = 0; k < M; ++k) c[k + 1] = c0p[k];
       double rp = 0.0;
 #pragma unroll
       for (int k = 0; k < M; ++k) {
-        const int s = s0 + k;
-        rp = fma(ML[s], c[k], fma(MD[s], c[k + 1], fma(MU[s], c[k + 2], -FS[s] * rp)));
+        rp = fma(co0[7 * k + 0], c[k], fma(co0[7 * k + 1], c[k + 1], fma(co0[7 * k + 2], c[k + 2], -co0[7 * k + 3] * rp)));
         Rr[k] = rp;
-        if (mb) P0 = fma(TQ[s], rp, P0);
+        if (mb) P0 = fma(co0[7 * k + 6], rp, P0);
       }
       Rp = rp;
       double b = Rr[M - 2];
 #pragma unroll
-      for (int k = M - 3; k >= 0; --k) b = Rr[k] - FG[s0 + k] * b;
+      for (int k = M - 3; k >= 0; --k) b = Rr[k] - co0[7 * k + 4] * b;
       bR = b;
     };
     if (fastM == 5) fwd_fast(std::integral_constant<int, 5>{});
@@ -379,16 +382,16 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
 #pragma unroll 2
         for (int k = 0; k < len; ++k, ++s) {
           const double c_next = (k == len - 1) ? c_halo_next : C[s + 1];
-          const double Rn = fma(ML[s], c_prev, fma(MD[s], c_self, fma(MU[s], c_next, -FS[s] * Rp)));
+          const double Rn = fma(CO[7 * (s) + 0], c_prev, fma(CO[7 * (s) + 1], c_self, fma(CO[7 * (s) + 2], c_next, -CO[7 * (s) + 3] * Rp)));
           C[s] = Rn;
-          P0 = fma(TQ[s], Rn, P0);
+          P0 = fma(CO[7 * (s) + 6], Rn, P0);
           Rp = Rn; c_prev = c_self; c_self = c_next;
         }
       } else {
 #pragma unroll 2
         for (int k = 0; k < len; ++k, ++s) {
           const double c_next = (k == len - 1) ? c_halo_next : C[s + 1];
-          const double Rn = fma(ML[s], c_prev, fma(MD[s], c_self, fma(MU[s], c_next, -FS[s] * Rp)));
+          const double Rn = fma(CO[7 * (s) + 0], c_prev, fma(CO[7 * (s) + 1], c_self, fma(CO[7 * (s) + 2], c_next, -CO[7 * (s) + 3] * Rp)));
           C[s] = Rn;
           Rp = Rn; c_prev = c_self; c_self = c_next;
         }
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
         int sb = s0 + (len - 2);
         bR = C[sb];
 #pragma unroll 1
-        for (int k = len - 3; k >= 0; --k) { --sb; bR = C[sb] - FG[sb] * bR; }
+        for (int k = len - 3; k >= 0; --k) { --sb; bR = C[sb] - CO[7 * (sb) + 4] * bR; }
       }
     }
     // right-hand side of the reduced system, row t = (Rp_t - r_Gp_t bR_{t+1}) r_inv_t in two parts: red0[t] = Rp_t r_inv_t by
@@ -438,9 +441,9 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
       double cn = sj;
       auto back_fast = [&](auto mtag) {
         constexpr int M = decltype(mtag)::value;
-        C[s0 + M - 1] = cn;
+        c0p[M - 1] = cn;
 #pragma unroll
-        for (int k = M - 2; k >= 0; --k) { cn = Rr[k] - FA[s0 + k] * sp - FG[s0 + k] * cn; C[s0 + k] = cn; }
+        for (int k = M - 2; k >= 0; --k) { cn = Rr[k] - co0[7 * k + 5] * sp - co0[7 * k + 4] * cn; c0p[k] = cn; }
       };
       if (fastM == 5) back_fast(std::integral_constant<int, 5>{});
       else if (fastM == 3) back_fast(std::integral_constant<int, 3>{});
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
         int sb = s0 + (len - 1);
         C[sb] = cn;
 #pragma unroll 2
-        for (int k = len - 2; k >= 0; --k) { --sb; cn = C[sb] - FA[sb] * sp - FG[sb] * cn; C[sb] = cn; }
+        for (int k = len - 2; k >= 0; --k) { --sb; cn = C[sb] - CO[7 * (sb) + 5] * sp - CO[7 * (sb) + 4] * cn; C[sb] = cn; }
       }
       hLast[tid] = sj; hFirst[tid] = cn;
       // finite check of the step (status 11) on the outer ends, by the chunks that own them
