@@ -141,9 +141,20 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
   double gi_prev = 0.0;                                     // r_Gp * r_inv of the previous chunk (0: none / it is a last chunk)
   const double *const co0 = CO + 7 * (size_t)s0;            // this chunk's rows of the factorisation and of the profile
   double *const c0p = C + s0;
-  double dt_full = 0.0, dtD_l = -1.0, dtD_r = -1.0;         // thread 0: cached find_dt
-  HistCache hc;
-  if (tid == 0) hist_load(hc, P, S.hidx);
+  // Chunks of 3 / 5 full rows keep their rows of the profile (cst) and of G (gk: read twice per step) in registers
+  // across the steps: the shared-memory pipe is what bounds this kernel (68 % busy at config 3's size with every row
+  // re-read from shared memory).  C in shared memory is brought up to date at the exit (and per step for the history).
+  const int fastM = (active && len == m && (m == 3 || m == 5)) ? m : 0;
+  const bool rec_on = (A.flags & F_RECORD) && A.rec;
+  double cst[5], gk[4];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) cst[k] = (k < fastM) ? c0p[k] : 0.0;
+  // thread 0's cached find_dt and history interval live in fields of the member scalars this kernel does not use otherwise
+  // (registers are what bounds the chunks' resident rows below)
+  double &dt_full = S.lp0, &dtD_l = S.lp1, &dtD_r = S.lp2;
+  auto hc_get = [&]() { HistCache h; h.i = S.nqL; h.x0 = S.lp3; h.x1 = S.lp4; h.iv = S.a_if; h.k0 = S.b_if; h.k1 = S.Co_first; h.T0 = S.Co_last; h.T1 = S.sdx; return h; };
+  auto hc_put = [&](const HistCache &h) { S.nqL = h.i; S.lp3 = h.x0; S.lp4 = h.x1; S.a_if = h.iv; S.b_if = h.k0; S.Co_first = h.k1; S.Co_last = h.T0; S.sdx = h.T1; };
+  if (tid == 0) { dt_full = 0.0; dtD_l = -1.0; dtD_r = -1.0; HistCache h0; hist_load(h0, P, S.hidx); hc_put(h0); }
 
   // ---- scalar batches (constant diffusivities): with V_ip == 0 and no Arrhenius law the per-step scalars do not depend
   // on the solution and dt only changes on the clipped last step, so thread 0 runs the time chain (t += dt, exact adds)
@@ -231,7 +242,9 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
       S.it += 1;
       if (S.t > S.t_tot) { S.dt = xsub(S.dt, xsub(S.t, S.t_tot)); S.t = S.t_tot; }
       double KD, Tt, Dl, Dr;
+      HistCache hc = hc_get();
       const int rc = chain_update_params(S, A, P, S.t, hc, &KD, &Tt, &Dl, &Dr);
+      hc_put(hc);
       if (rc) S.status = rc;
       else {
         S.KD = KD; S.T = Tt; S.D_l = Dl; S.D_r = Dr;
@@ -319,7 +332,11 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
       red1c[tid] = red1[tid];
       gi_prev = (tid > 0) ? exA[tid - 1] : 0.0;
       __syncthreads();                         // redS | redD, redU, exR change roles: step-time arrays from here
-      if (active) { hFirst[tid] = C[s0]; hLast[tid] = C[s0 + len - 1]; }
+      if (fastM) {
+        hFirst[tid] = cst[0]; hLast[tid] = (fastM == 3) ? cst[2] : cst[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gk[k] = (k < fastM - 1) ? co0[7 * k + 4] : 0.0;
+      } else if (active) { hFirst[tid] = C[s0]; hLast[tid] = C[s0 + len - 1]; }
       redB[red_ix<T>(tid)] = 0.0;
       __syncthreads();
       if (bc == BC_FLUX) {
@@ -339,7 +356,7 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
     // Two block barriers per step (flux / hold; the mass-balance row adds its block sum): chunks exchange their end values
     // through hFirst / hLast, so the sweep reads and writes only its own rows of C; the reduced right-hand side is
     // assembled from two contributions (the chunk's own: red0, its right-hand neighbour's: redB) without a barrier between
-    // them.  Chunks of 3 / 5 / 7 full rows run straight-line code with the rows of the elimination in registers.
+    // them.  Chunks of 3 / 5 full rows run straight-line code with the rows of the elimination in registers.
     const int p = n1 - 1, q = N - 1;         // interface nodes (the right one is the last element of the reversed block)
     const double a_old = C[p], b_old = C[q];
     double c_halo_prev = 0.0, c_halo_next = 0.0;
@@ -349,14 +366,13 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
     }
     const int rix = red_ix<T>(tid), rixm = red_ix<T>(tid > 0 ? tid - 1 : 0);
     double P0 = 0.0, Rp = 0.0, bR = 0.0;
-    double Rr[7];                             // rows of the elimination of a 3 / 5 / 7-row chunk
-    const int fastM = (active && len == m && (m == 3 || m == 5 || m == 7)) ? m : 0;
+    double Rr[5];                             // rows of the elimination of a 3 / 5-row chunk
     auto fwd_fast = [&](auto mtag) {
       constexpr int M = decltype(mtag)::value;
       double c[M + 2];
       c[0] = c_halo_prev; c[M + 1] = c_halo_next;
 #pragma unroll
-      for (int k = 0; k < M; ++k) c[k + 1] = c0p[k];
+      for (int k = 0; k < M; ++k) c[k + 1] = cst[k];
       double rp = 0.0;
 #pragma unroll
       for (int k = 0; k < M; ++k) {
@@ -367,12 +383,11 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
       Rp = rp;
       double b = Rr[M - 2];
 #pragma unroll
-      for (int k = M - 3; k >= 0; --k) b = Rr[k] - co0[7 * k + 4] * b;
+      for (int k = M - 3; k >= 0; --k) b = Rr[k] - gk[k] * b;
       bR = b;
     };
     if (fastM == 5) fwd_fast(std::integral_constant<int, 5>{});
     else if (fastM == 3) fwd_fast(std::integral_constant<int, 3>{});
-    else if (fastM == 7) fwd_fast(std::integral_constant<int, 7>{});
     else if (active) {
       double c_prev = c_halo_prev, c_self = C[s0];
       int s = s0;
@@ -441,13 +456,16 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
       double cn = sj;
       auto back_fast = [&](auto mtag) {
         constexpr int M = decltype(mtag)::value;
-        c0p[M - 1] = cn;
+        cst[M - 1] = cn;
 #pragma unroll
-        for (int k = M - 2; k >= 0; --k) { cn = Rr[k] - co0[7 * k + 5] * sp - co0[7 * k + 4] * cn; c0p[k] = cn; }
+        for (int k = M - 2; k >= 0; --k) { cn = Rr[k] - co0[7 * k + 5] * sp - gk[k] * cn; cst[k] = cn; }
+        if (rec_on) {
+#pragma unroll
+          for (int k = 0; k < M; ++k) c0p[k] = cst[k];
+        }
       };
       if (fastM == 5) back_fast(std::integral_constant<int, 5>{});
       else if (fastM == 3) back_fast(std::integral_constant<int, 3>{});
-      else if (fastM == 7) back_fast(std::integral_constant<int, 7>{});
       else {
         int sb = s0 + (len - 1);
         C[sb] = cn;
@@ -464,7 +482,7 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
       S.steps += 1;
     }
     __syncthreads();
-    if ((A.flags & F_RECORD) && A.rec) {
+    if (rec_on) {
       double v[4] = {0.0, 0.0, 0.0, 0.0};
       for (int i = tid; i < n1 - 1; i += T)
         v[0] += 0.5 * (S.rho1 * powd<NDIM>(X[i + 1]) - S.rho1 * powd<NDIM>(X[i])) * (C[i] + C[i + 1]);
@@ -478,6 +496,8 @@ __global__ void __launch_bounds__(T, MBM_FIXED_WARPS * 32 / T) mbm_fixed_kernel(
       __syncthreads();
     }
   }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) if (k < fastM) c0p[k] = cst[k];
   __syncthreads();
   // ---------------- store member ----------------
   {
