@@ -242,7 +242,15 @@ def main():
     bad = int((dtens["status"] != 0).sum().item())
     tsec = torch.tensor([secs], device=dev, dtype=torch.float64)
     tns = torch.tensor([float(ns), float(bad)], device=dev, dtype=torch.float64)
+    per_rank = None
     if world > 1:
+        # every rank's own time, node-steps and SM clock (its own GPU, sampled during its timed region): shows whether a
+        # max-over-ranks time above the single-GPU one is imbalance between the ranks' ensembles or a slower GPU
+        mine = torch.tensor([secs, float(ns), float(clocks["sm_mhz"] or 0.0)], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [1e3 * float(a[0].item()) / max(args.steps, 1) for a in allr],
+                    "node_steps": [float(a[1].item()) for a in allr], "sm_mhz": [float(a[2].item()) for a in allr]}
         dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
         dist.all_reduce(tns, op=dist.ReduceOp.SUM)
     secs_max, ns_all, bad_all = float(tsec.item()), float(tns[0].item()), int(tns[1].item())
@@ -339,6 +347,8 @@ def main():
         "config": workload_config(args), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches, "clocks": clocks, "node_steps_timed": ns_all, "members_failed": bad_all,
     }
+    if per_rank:
+        line["per_rank"] = per_rank
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
