@@ -290,10 +290,12 @@ int mbm_set_stream(void *cuda_stream);
 double mbm_measure_dfma_tflops(int device);
 
 /* CUDA library only (oracle: zeros).  Diagnostics of the streaming kernel for long uniform meshes
- * (MRefin == 1, closed-form meshes): member-steps of `device` since the library was loaded that took the fused
+ * (MRefin == 1, closed-form meshes), counted on `device` since the library was loaded: member-steps that took the fused
  * back-substitution + regrid pass / the two-pass path (node counts or layout changed by regrid!,
- * functions.jl:873-889).  Tests use it to check which path ran.  Returns 0, or MBM_RC_CUDA.           */
-int mbm_stream_pass_counts(int device, uint64_t *fused_steps, uint64_t *twopass_steps);
+ * functions.jl:873-889; fixed-interface steps), and the chunk rows (summed over member-steps) that were stored
+ * without their fill-in value (below 1e-19).  Tests use it to check which path ran.  Any pointer may be NULL.
+ * Returns 0, or MBM_RC_CUDA.                                                                          */
+int mbm_stream_pass_counts(int device, uint64_t *fused_steps, uint64_t *twopass_steps, uint64_t *rows_without_fill_in);
 
 #ifdef __cplusplus
 }

@@ -145,7 +145,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.mbm_validate_batch.restype = C.c_int
     lib.mbm_validate_batch.argtypes = [C.POINTER(ValidateArgs)]
     lib.mbm_stream_pass_counts.restype = C.c_int
-    lib.mbm_stream_pass_counts.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.mbm_stream_pass_counts.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     return lib
 
 

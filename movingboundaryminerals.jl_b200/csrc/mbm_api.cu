@@ -459,6 +459,7 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
       // closed-form meshes first (only the concentrations cross HBM); members whose x arrays are not LinRanges are
       // handed on (status -1) to the kernel that keeps x in memory
       if (!getenv("MBM_NO_STREAM2")) {
+        if (getenv("MBM_S2_NO_CUTOFF")) AS.flags |= mbm::F_DEV_S2_NO_CUTOFF;      // (tests: every row keeps its fill-in)
         rc = launch_stream2(AS, m0 + off, n, s);
         if (rc) return rc;
         ++launches;
@@ -798,17 +799,19 @@ double mbm_measure_dfma_tflops(int device) {
   return best;
 }
 int64_t mbm_last_kernel_launches(void) { return g_last_kernel_launches_any; }
-int mbm_stream_pass_counts(int device, uint64_t *fused_steps, uint64_t *twopass_steps) {
+int mbm_stream_pass_counts(int device, uint64_t *fused_steps, uint64_t *twopass_steps, uint64_t *rows_without_fill_in) {
   int prev = 0;
   if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) return MBM_RC_CUDA;
-  unsigned long long f = 0, t = 0;
+  unsigned long long f = 0, t = 0, r = 0;
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpyFromSymbol(&f, mbm::g_s2_fused_steps, sizeof(f));
   if (e == cudaSuccess) e = cudaMemcpyFromSymbol(&t, mbm::g_s2_twopass_steps, sizeof(t));
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(&r, mbm::g_s2_cut_rows, sizeof(r));
   cudaSetDevice(prev);
   if (e != cudaSuccess) return MBM_RC_CUDA;
   if (fused_steps) *fused_steps = f;
   if (twopass_steps) *twopass_steps = t;
+  if (rows_without_fill_in) *rows_without_fill_in = r;
   return 0;
 }
 

@@ -40,7 +40,7 @@ constexpr int S2_MAX_FIX = 10;            // most deferred nodes per column the 
 constexpr double S2_A_DROP = 1e-19, S2_A_ZERO = 1e-21;
 
 // diagnostics (tests): steps taken by the fused pass / by the two-pass path since the library was loaded
-__device__ unsigned long long g_s2_fused_steps = 0ull, g_s2_twopass_steps = 0ull;
+__device__ unsigned long long g_s2_fused_steps = 0ull, g_s2_twopass_steps = 0ull, g_s2_cut_rows = 0ull;
 
 // RN(i/d) for integers 0 <= i <= d <= S2_MAX_D, r = RN(1/d): q0 = i*r is within an ulp of the quotient, the remainder
 // i - q0*d is exact in one FMA, and the corrected quotient rounds correctly (checked exhaustively)
@@ -476,9 +476,7 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
     __syncthreads();
     // rows k < Kc: (R, A, G) at 3 k T; rows k >= Kc: (R, G) at 3 Kc T + 2 (k - Kc) T
     int Kc = s2_Kc;
-#ifdef MBM_S2_NO_CUTOFF
-    Kc = 0x3fffffff;
-#endif
+    if (A.flags & F_DEV_S2_NO_CUTOFF) Kc = 0x3fffffff;
     auto row_ptr = [&](const int k) { return RAG + ((k < Kc) ? (size_t)k * (3 * T) : (size_t)Kc * (3 * T) + (size_t)(k - Kc) * (2 * T)) + tid; };
     for (int attempt = 0;; ++attempt) {
       Ap = 0.0; Gp = 0.0; Rp = 0.0; P0 = 0.0; Qa = 0.0; Qc = 0.0;
@@ -593,6 +591,7 @@ __global__ void __launch_bounds__(T, MBM_STREAM_MINB) mbm_stream2_kernel(const K
         if (tid == 0) s2_Kc = Kc;
         continue;
       }
+      if (tid == 0 && Kc < m) atomicAdd(&g_s2_cut_rows, (unsigned long long)(m - Kc));
       kz = min(kz, len);                       // columns shorter than their cutoff do not count
       for (int o_ = 16; o_ > 0; o_ >>= 1) kz = max(kz, __shfl_xor_sync(0xffffffffu, kz, o_));
       if (lane == 0) atomicMax(&s2_kz, kz);

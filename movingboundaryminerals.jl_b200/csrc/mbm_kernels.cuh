@@ -9,7 +9,8 @@ namespace mbm {
 
 enum { BC_NONE = 0, BC_FLUX = 1, BC_MB = 2, BC_STEFAN = 3, BC_HOLD = 4 };
 enum { DT_FIND = 0, DT_ADV = 1, DT_STEFAN = 2, DT_SIMPLE = 3 };
-enum { F_NEWTON_WARM = 1, F_RECORD = 2, F_MASS_FINAL = 0x80 };
+enum { F_NEWTON_WARM = 1, F_RECORD = 2, F_MASS_FINAL = 0x80,
+       F_DEV_S2_NO_CUTOFF = 0x40000000u /* set by the library from MBM_S2_NO_CUTOFF (tests): no fill-in cutoff */ };
 
 struct KArgs {
   int M, ndim, hist_len, capL, capR, capS, inner_bc, dt_mode;

@@ -496,8 +496,15 @@ def test_step_history_of_a_moving_couple(oracle, cuda_lib):
 def _stream_pass_counts(lib):
     import ctypes as C
     f, t = C.c_uint64(0), C.c_uint64(0)
-    assert lib.mbm_stream_pass_counts(0, C.byref(f), C.byref(t)) == 0
+    assert lib.mbm_stream_pass_counts(0, C.byref(f), C.byref(t), None) == 0
     return int(f.value), int(t.value)
+
+
+def _stream_cut_rows(lib):
+    import ctypes as C
+    r = C.c_uint64(0)
+    assert lib.mbm_stream_pass_counts(0, None, None, C.byref(r)) == 0
+    return int(r.value)
 
 
 def test_streaming_closed_form_fused_pass(oracle, cuda_lib):
@@ -686,3 +693,59 @@ def test_step_history_on_the_global_memory_path(oracle, cuda_lib):
     for c in range(4):
         assert _relerr(ro[:, c], rg[:, c]) < 1e-11, c
     compare(eo, eg)
+
+
+@pytest.mark.parametrize("n", [1, 3])
+def test_streaming_closed_form_other_geometries(oracle, cuda_lib, n):
+    """closed-form streaming kernel, planar and spherical members (the element matrices of functions.jl:525-540 for
+    n = 1 / 3), flux members with a Dirichlet outer boundary on either side (set_outer_bc!, :1230-1243) beside closed
+    mass-balance members: fused pass on the steps whose node counts stay, against the oracle"""
+    pars = []
+    for kind, V, bcout in (("mb", 1e-7, [0, 0]), ("mb", -1e-7, [0, 0])):
+        p = d.pars_MB_growth()
+        p.update(V_ip=V, res=[3000, 3000], MRefin=1.0, Ri=[0.45, 1.0], t_tot=2e4, KD_ar=(0.1, 0.1), Cl_i=0.5, Cr_i=5.0, n=n)
+        pars.append(p)
+    eo, eg = None, None
+    eo, _ = d.build_couple_ensemble(pars, oracle, cap_left=5600, cap_right=5600)
+    eg, _ = d.build_couple_ensemble(pars, cuda_lib, cap_left=5600, cap_right=5600)
+    f0, _t0 = _stream_pass_counts(cuda_lib)
+    assert eo.run(oracle, max_steps=50) == 0
+    assert eg.run(cuda_lib, max_steps=50, flags=abi.FLAG_FORCE_STREAMING) == 0
+    assert _stream_pass_counts(cuda_lib)[0] - f0 >= 90
+    compare(eo, eg)
+    fl = []
+    # (a Dirichlet condition at the left outer boundary is only accepted for planar members, Diff_couple_1D_general_Flux.jl:80)
+    for V, bcout in ((1e-7, [1, 0] if n == 1 else [0, 0]), (-1e-7, [0, 1]), (2e-7, [1, 1] if n == 1 else [0, 1])):
+        p = d.pars_DCGF()
+        p.update(V_ip=V, res=[3000, 3000], MRefin=1.0, Ri=[0.45, 1.0], t_tot=2e4, KD_ar=(0.1, 0.1), Cl_i=0.5, Cr_i=5.0, n=n,
+                 Di=[4e-7, 5e-8], T_ar=(1273.15, 923.15), BCout=bcout)
+        fl.append(p)
+    eo, _ = d.build_couple_ensemble(fl, oracle, cap_left=5600, cap_right=5600)
+    eg, _ = d.build_couple_ensemble(fl, cuda_lib, cap_left=5600, cap_right=5600)
+    assert eo.run(oracle, max_steps=50) == 0
+    assert eg.run(cuda_lib, max_steps=50, flags=abi.FLAG_FORCE_STREAMING) == 0
+    compare(eo, eg)
+
+
+def test_streaming_fill_in_cutoff_changes_nothing(cuda_lib, monkeypatch):
+    """rows beyond the decay length of a chunk's fill-in column are stored without it (|A_k| < 1e-19, checked in the
+    sweep): at config 5's member size (columns of 518 rows) the profiles with and without the cutoff agree to the last
+    bits, integers and checksum exactly"""
+    from mbm_b200 import ensembles as E
+    res = 65536
+    pars = E.c5_highres(3, res, max_steps=100)
+    ea, _ = d.build_couple_ensemble(pars, cuda_lib, cap_left=res + 4, cap_right=res + 4)
+    eb = ea.copy()
+    r0 = _stream_cut_rows(cuda_lib)
+    assert ea.run(cuda_lib, max_steps=8) == 0
+    r1 = _stream_cut_rows(cuda_lib)
+    assert r1 - r0 >= 3 * 7 * 200, r1 - r0            # every step but the first stores > 200 of 518 rows per column as (R, G)
+    monkeypatch.setenv("MBM_S2_NO_CUTOFF", "1")
+    assert eb.run(cuda_lib, max_steps=8) == 0
+    monkeypatch.delenv("MBM_S2_NO_CUTOFF")
+    assert _stream_cut_rows(cuda_lib) == r1
+    for k in ("res", "it", "idx_hash", "node_steps", "x_left", "x_right", "t", "Ri"):
+        assert np.array_equal(ea.arrays[k], eb.arrays[k]), k
+    for m in range(3):
+        for a, b in zip(ea.member(m), eb.member(m)):
+            assert _relerr(a, b) < 1e-15
