@@ -21,8 +21,14 @@
 //    regrid!, a layout change - is redone by the two-pass path (back-substitution, then the interval-driven walk of the
 //    first streaming kernel on closed-form meshes), which is also the path of short columns.
 //
-// Traffic per node-step: forward sweep reads C, writes A, G, R (32 B); fused pass reads A, G, R, writes the new C (32 B):
-// 64 B against the 104 B of the first streaming kernel (algorithmic figure, SURVEY.md §8(d): 32 B with x, 16 B without).
+//  * ROWS OF THE ELIMINATION interleaved row by row (one row pointer, immediate offsets, one bulk copy per batch), batches
+//    of interior rows as straight-line code, and a FILL-IN CUTOFF: beyond the decay length of a chunk's fill-in column the
+//    rows are stored as (R, G) pairs (see S2_A_DROP below).  Fixed-interface members (V_ip == 0) run the same kernel
+//    without the regrid.
+//
+// Traffic per node-step: forward sweep reads C, writes (R, A, G) or (R, G); second pass reads them back, writes the new C:
+// ~54 B (64 B without the cutoff) against the 104 B of the first streaming kernel (algorithmic figure, SURVEY.md §8(d):
+// 32 B with x, 16 B for C alone).
 #pragma once
 #include <type_traits>
 #include "mbm_kernel_stream.cuh"
