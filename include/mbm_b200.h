@@ -37,7 +37,12 @@ enum {
   MBM_BC_FLUX           = 1, /* set_inner_bc_flux!   src/functions.jl:1054-1072               */
   MBM_BC_MB             = 2, /* set_inner_bc_mb!     src/functions.jl:1094-1109               */
   MBM_BC_STEFAN         = 3, /* set_inner_bc_stefan! src/functionsStefan.jl:131-144           */
-  MBM_BC_DIRICHLET_HOLD = 4  /* inline rows, examples/Diff_couple_no_interaction.jl:108-118   */
+  MBM_BC_DIRICHLET_HOLD = 4, /* inline rows, examples/Diff_couple_no_interaction.jl:108-118   */
+  MBM_BC_LASAGA = 5          /* set_inner_bc_Lasaga!, src/functions.jl:1143-1206 (major-element exchange after Lasaga 1983):
+                                both interface values prescribed from the step's OLD neighbour values, KD, D, rho and the
+                                two interface spacings (closed-form roots sol1 / sol2 with the reference's own selection rule,
+                                including sol2's product where sol1 divides, :1187); the reference exports the function but
+                                ships no driver for it: the loop is DCGF's with this row function.  pow(.,1/2) is sqrt.   */
 };
 
 /* ---- time-step rule ----------------------------------------------------------------- */

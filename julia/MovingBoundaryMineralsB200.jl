@@ -15,7 +15,7 @@ using MovingBoundaryMinerals: scaling, rescale            # host-side pre/post s
 
 const LIB = get(ENV, "MBM_B200_LIB", joinpath(@__DIR__, "..", "movingboundaryminerals.jl_b200", "csrc", "libmbm_b200.so"))
 const ABI_VERSION = Int32(3)
-const BC_FLUX, BC_MB, BC_STEFAN, BC_HOLD = Int32(1), Int32(2), Int32(3), Int32(4)
+const BC_FLUX, BC_MB, BC_STEFAN, BC_HOLD, BC_LASAGA = Int32(1), Int32(2), Int32(3), Int32(4), Int32(5)
 const DT_FIND_DT, DT_ADVECTIVE, DT_STEFAN, DT_SIMPLE = Int32(0), Int32(1), Int32(2), Int32(3)
 const FLAG_RECORD, FLAG_MASS_FINAL = UInt32(0x0002), UInt32(0x0080)
 
@@ -119,7 +119,7 @@ function couple_ensemble(pars::AbstractVector; kind::Symbol = :mb, dt_mode::Int3
     rc == 0 || error("mbm_calc_mass_vol failed rc=$rc")
     t = zeros(M); dt = zeros(M); it = zeros(Int64, M); Mass = zeros(M); last = zeros(8, M)
     warn = zeros(Int32, M); hash = zeros(UInt64, M); node_steps = zeros(Int64, M)
-    inner = kind === :mb ? BC_MB : kind === :flux ? BC_FLUX : BC_HOLD
+    inner = kind === :mb ? BC_MB : kind === :flux ? BC_FLUX : kind === :lasaga ? BC_LASAGA : BC_HOLD
     GC.@preserve Di D0 Ea rho V ttot CFL MRefin BCout resmin t_ar T_ar KD_ar x_left C_left x_right C_right res Ri t dt it dx1 dx2 Mass0 Mass nR last status warn hash node_steps begin
         c = Ref(Common(ABI_VERSION, M, n, H, capL, capR, inner, dt_mode, FLAG_MASS_FINAL, Int32(n_devices), max_steps, C_NULL, 0))
         p = Ref(CoupleParams(pointer(Di), pointer(D0), pointer(Ea), pointer(rho), pointer(V), pointer(ttot), pointer(CFL),

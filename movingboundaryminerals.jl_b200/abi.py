@@ -15,7 +15,7 @@ ABI_VERSION = 3
 LAW_NONE, LAW_OLIVINE_MELT_D1 = 0, 1      # mbm_couple_params.law (examples/D1.jl:126-132)
 
 # interface conditions / dt rules / flags (include/mbm_b200.h)
-BC_NONE, BC_FLUX, BC_MB, BC_STEFAN, BC_DIRICHLET_HOLD = 0, 1, 2, 3, 4
+BC_NONE, BC_FLUX, BC_MB, BC_STEFAN, BC_DIRICHLET_HOLD, BC_LASAGA = 0, 1, 2, 3, 4, 5
 DT_FIND_DT, DT_ADVECTIVE, DT_STEFAN, DT_SIMPLE = 0, 1, 2, 3
 FLAG_NEWTON_WARM = 0x0001
 FLAG_RECORD = 0x0002

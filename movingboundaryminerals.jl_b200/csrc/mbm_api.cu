@@ -838,7 +838,7 @@ int mbm_couple_batch(const mbm_common *c, const mbm_couple_params *p, mbm_couple
   int rc = check_common(c);
   if (rc) return rc;
   if (!p || !io || c->cap_right < 3) return MBM_RC_BAD_ARG;
-  if (c->inner_bc < MBM_BC_FLUX || c->inner_bc > MBM_BC_DIRICHLET_HOLD) return MBM_RC_BAD_ARG;
+  if (c->inner_bc < MBM_BC_FLUX || c->inner_bc > MBM_BC_LASAGA) return MBM_RC_BAD_ARG;
   if (!p->Di || !p->rho || !p->t_tot || !p->CFL || !p->MRefin || !p->BCout || !p->resmin || !p->t_ar || !p->T_ar)
     return MBM_RC_BAD_ARG;
   if (c->inner_bc != MBM_BC_STEFAN && !p->KD_ar) return MBM_RC_BAD_ARG;
@@ -864,7 +864,7 @@ int mbm_couple_batch(const mbm_common *c, const mbm_couple_params *p, mbm_couple
 }
 
 int mbm_couple_flux_batch(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io *io) {
-  if (!c || (c->inner_bc != MBM_BC_FLUX && c->inner_bc != MBM_BC_DIRICHLET_HOLD)) return MBM_RC_BAD_ARG;
+  if (!c || (c->inner_bc != MBM_BC_FLUX && c->inner_bc != MBM_BC_DIRICHLET_HOLD && c->inner_bc != MBM_BC_LASAGA)) return MBM_RC_BAD_ARG;
   return mbm_couple_batch(c, p, io);
 }
 int mbm_couple_mb_batch(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io *io) {

@@ -7,7 +7,7 @@
 
 namespace mbm {
 
-enum { BC_NONE = 0, BC_FLUX = 1, BC_MB = 2, BC_STEFAN = 3, BC_HOLD = 4 };
+enum { BC_NONE = 0, BC_FLUX = 1, BC_MB = 2, BC_STEFAN = 3, BC_HOLD = 4, BC_LASAGA = 5 };
 enum { DT_FIND = 0, DT_ADV = 1, DT_STEFAN = 2, DT_SIMPLE = 3 };
 enum { F_NEWTON_WARM = 1, F_RECORD = 2, F_MASS_FINAL = 0x80,
        F_DEV_S2_NO_CUTOFF = 0x40000000u /* set by the library from MBM_S2_NO_CUTOFF (tests): no fill-in cutoff */ };
@@ -600,6 +600,59 @@ __device__ __forceinline__ double pchip_eval_one(const double *x, const double *
 }
 
 
+
+// set_inner_bc_Lasaga! (src/functions.jl:1143-1206): both interface values from the step's old neighbour values - sol1 / sol2
+// with the reference's selection rule (:1189-1193; sol2 multiplies by the denominator where sol1 divides, :1187) and
+// BC_left (:1194).  Operation for operation as oracle lasaga_bc (never contracted; the square root is correctly rounded on
+// both sides), so the prescribed values are bit-identical.
+__device__ __noinline__ void lasaga_bc(double cl, double cr, double Dl, double Dr, double K, double d1, double d2, double r1,
+                                       double r2, double *bc_left, double *bc_right) {
+  const double cl2 = xmul(cl, cl), cr2 = xmul(cr, cr), Dl2 = xmul(Dl, Dl), Dr2 = xmul(Dr, Dr), K2 = xmul(K, K),
+               d12 = xmul(d1, d1), d22 = xmul(d2, d2), r12 = xmul(r1, r1), r22 = xmul(r2, r2);
+  auto p5 = [](double a, double b, double c, double d, double e) { return xmul(xmul(xmul(xmul(a, b), c), d), e); };
+  auto p6 = [](double a, double b, double c, double d, double e, double f) { return xmul(xmul(xmul(xmul(xmul(a, b), c), d), e), f); };
+  auto p9 = [](double a, double b, double c, double d, double e, double f, double g, double h, double i) {
+    return xmul(xmul(xmul(xmul(xmul(xmul(xmul(xmul(a, b), c), d), e), f), g), h), i);
+  };
+  auto p10 = [](double a, double b, double c, double d, double e, double f, double g, double h, double i, double j) {
+    return xmul(xmul(xmul(xmul(xmul(xmul(xmul(xmul(xmul(a, b), c), d), e), f), g), h), i), j);
+  };
+  double rad = p5(cl2, Dl2, K2, d22, r12);
+  rad = xsub(rad, p6(2.0, cl2, Dl2, K, d22, r12));
+  rad = xadd(rad, xmul(xmul(xmul(cl2, Dl2), d22), r12));
+  rad = xadd(rad, p10(2.0, cl, cr, Dl, Dr, K2, d1, d2, r1, r2));
+  rad = xsub(rad, p10(4.0, cl, cr, Dl, Dr, K, d1, d2, r1, r2));
+  rad = xadd(rad, p9(2.0, cl, cr, Dl, Dr, d1, d2, r1, r2));
+  rad = xsub(rad, p6(2.0, cl, Dl2, K2, d22, r12));
+  rad = xadd(rad, p6(2.0, cl, Dl2, K, d22, r12));
+  rad = xadd(rad, p9(2.0, cl, Dl, Dr, K, d1, d2, r1, r2));
+  rad = xsub(rad, xmul(xmul(xmul(xmul(xmul(xmul(xmul(2.0, cl), Dl), Dr), d1), d2), r1), r2));
+  rad = xadd(rad, p5(cr2, Dr2, K2, d12, r22));
+  rad = xsub(rad, p6(2.0, cr2, Dr2, K, d12, r22));
+  rad = xadd(rad, xmul(xmul(xmul(cr2, Dr2), d12), r22));
+  rad = xsub(rad, p9(2.0, cr, Dl, Dr, K2, d1, d2, r1, r2));
+  rad = xadd(rad, p9(2.0, cr, Dl, Dr, K, d1, d2, r1, r2));
+  rad = xadd(rad, p6(2.0, cr, Dr2, K, d12, r22));
+  rad = xsub(rad, p5(2.0, cr, Dr2, d12, r22));
+  rad = xadd(rad, xmul(xmul(xmul(Dl2, K2), d22), r12));
+  rad = xadd(rad, xmul(xmul(xmul(xmul(xmul(xmul(xmul(2.0, Dl), Dr), K), d1), d2), r1), r2));
+  rad = xadd(rad, xmul(xmul(Dr2, d12), r22));
+  const double root = __dsqrt_rn(rad);
+  const double Drd1r2 = xmul(xmul(Dr, d1), r2);
+  const double den = xmul(2.0, xsub(Drd1r2, xmul(xmul(xmul(Dr, K), d1), r2)));
+  const double t_a = xmul(xmul(xmul(cl, Dl), d2), r1), t_b = xmul(xmul(xmul(cr, Dr), d1), r2), t_c = xmul(xmul(xmul(Dl, K), d2), r1);
+  const double t_d = xmul(xmul(xmul(xmul(cl, Dl), K), d2), r1), t_e = xmul(xmul(xmul(xmul(cr, Dr), K), d1), r2);
+  double n1 = xsub(Drd1r2, root);
+  n1 = xadd(n1, t_a); n1 = xadd(n1, t_b); n1 = xadd(n1, t_c); n1 = xsub(n1, t_d); n1 = xsub(n1, t_e);
+  const double sol1 = xmul(n1, xinv(den));
+  double n2 = xadd(root, Drd1r2);
+  n2 = xadd(n2, t_a); n2 = xadd(n2, t_b); n2 = xadd(n2, t_c); n2 = xsub(n2, t_d); n2 = xsub(n2, t_e);
+  const double sol2 = xmul(n2, den);
+  const double br = (sol2 > 1.0 || sol2 < 0.0) ? sol1 : sol2;
+  *bc_right = br;
+  *bc_left = xsub(cl, xmul(xmul(xmul(Dr, d1), xinv(xmul(Dl, d2))), xsub(br, cr)));
+}
+
 // ---- value-code variants used by the tuned kernel (fast reciprocal, walking interval search) -----------
 __device__ __forceinline__ double slope_interior(double ihm, double ihp, double mm, double mp) {
   // d = (w- m- + w+ m+)/(w- + w+), w = 2/h (the factor 2 cancels); zero on sign change / zero secant; limiter 3*min|m|
@@ -1093,6 +1146,8 @@ __global__ void __launch_bounds__(T, (T <= 64) ? 512 / T : 1) mbm_step_kernel(co
     const double Co_last = C[SIDX(N - 1)];
     const double a_old = simple ? 0.0 : C[SIDX(p)];
     const double b_old = simple ? 0.0 : C[SIDX(q)];
+    // (set_inner_bc_Lasaga! prescribes the interface values from the old neighbours of the interface nodes)
+    const double las_cl = (bc == BC_LASAGA) ? C[SIDX(p - 1)] : 0.0, las_cr = (bc == BC_LASAGA) ? C[SIDX(q + 1)] : 0.0;
     double c_halo_prev = 0.0, c_halo_next = 0.0;
     if (active) {
       if (f > 0) c_halo_prev = C[LOCS(f - 1)];
@@ -1243,6 +1298,9 @@ __global__ void __launch_bounds__(T, (T <= 64) ? 512 / T : 1) mbm_step_kernel(co
         const double wq = 0.5 * (pow_ndim(X[SIDX(q + 1)], ndim) - Vq_) + 0.5 * (Vq_ - Vp_);
         bif = (S.Mass0 - (v[0] + v[2])) * frcp_((v[1] + wp) * S.KD + (v[3] + wq));
         aif = S.KD * bif;
+      } else if (bc == BC_LASAGA) {
+        const double dxl = xsub(X[SIDX(p)], X[SIDX(p - 1)]), dxr = xsub(X[SIDX(q + 1)], X[SIDX(q)]);
+        lasaga_bc(las_cl, las_cr, S.D_l, S.D_r, S.KD, dxl, dxr, S.rho1, S.rho2, &aif, &bif);
       } else {
         aif = a_old; bif = b_old;
       }

@@ -105,7 +105,8 @@ def pars_DCNI():
                 scale=False, dt_mode=abi.DT_FIND_DT, init="dcni")
 
 
-_KIND = {"flux": abi.BC_FLUX, "mb": abi.BC_MB, "hold": abi.BC_DIRICHLET_HOLD, "stefan": abi.BC_STEFAN}
+_KIND = {"flux": abi.BC_FLUX, "mb": abi.BC_MB, "hold": abi.BC_DIRICHLET_HOLD, "stefan": abi.BC_STEFAN,
+         "lasaga": abi.BC_LASAGA}
 
 DCNI_MODES_L = (np.array([1, 2, 5, 7, 12.0]), np.array([12, 0.5, 3, -2, 1.0]))
 DCNI_MODES_R = (np.array([1, 2, 3.0]), np.array([1, 8.0, 1 * (1.0 / 3.0)]))

@@ -49,6 +49,48 @@
 /* Julia arithmetic helpers                                                                    */
 /* ------------------------------------------------------------------------------------------ */
 static inline double jl_inv(double x) { return 1.0 / x; }
+
+/* set_inner_bc_Lasaga!, src/functions.jl:1143-1206: the numerical part (sol1, sol2, selection :1189-1193, BC_left :1194),
+ * term by term and left to right as Julia evaluates the expression (x^2 = x*x, Base.literal_pow; ^(1*inv(2)) restated
+ * as sqrt); cl = C_left[end-1], cr = C_right[2] (old values), d1, d2 = interface spacings, r1, r2 = rho[1], rho[2] */
+static void lasaga_bc(double cl, double cr, double Dl, double Dr, double K, double d1, double d2, double r1, double r2,
+                      double *bc_left, double *bc_right) {
+  const double cl2 = cl * cl, cr2 = cr * cr, Dl2 = Dl * Dl, Dr2 = Dr * Dr, K2 = K * K, d12 = d1 * d1, d22 = d2 * d2,
+               r12 = r1 * r1, r22 = r2 * r2;
+  double rad = cl2 * Dl2 * K2 * d22 * r12;
+  rad = rad - 2 * cl2 * Dl2 * K * d22 * r12;
+  rad = rad + cl2 * Dl2 * d22 * r12;
+  rad = rad + 2 * cl * cr * Dl * Dr * K2 * d1 * d2 * r1 * r2;
+  rad = rad - 4 * cl * cr * Dl * Dr * K * d1 * d2 * r1 * r2;
+  rad = rad + 2 * cl * cr * Dl * Dr * d1 * d2 * r1 * r2;
+  rad = rad - 2 * cl * Dl2 * K2 * d22 * r12;
+  rad = rad + 2 * cl * Dl2 * K * d22 * r12;
+  rad = rad + 2 * cl * Dl * Dr * K * d1 * d2 * r1 * r2;
+  rad = rad - 2 * cl * Dl * Dr * d1 * d2 * r1 * r2;
+  rad = rad + cr2 * Dr2 * K2 * d12 * r22;
+  rad = rad - 2 * cr2 * Dr2 * K * d12 * r22;
+  rad = rad + cr2 * Dr2 * d12 * r22;
+  rad = rad - 2 * cr * Dl * Dr * K2 * d1 * d2 * r1 * r2;
+  rad = rad + 2 * cr * Dl * Dr * K * d1 * d2 * r1 * r2;
+  rad = rad + 2 * cr * Dr2 * K * d12 * r22;
+  rad = rad - 2 * cr * Dr2 * d12 * r22;
+  rad = rad + Dl2 * K2 * d22 * r12;
+  rad = rad + 2 * Dl * Dr * K * d1 * d2 * r1 * r2;
+  rad = rad + Dr2 * d12 * r22;
+  const double root = sqrt(rad);
+  const double den = 2 * (Dr * d1 * r2 - Dr * K * d1 * r2);
+  double n1 = Dr * d1 * r2 - root;
+  n1 = n1 + cl * Dl * d2 * r1; n1 = n1 + cr * Dr * d1 * r2; n1 = n1 + Dl * K * d2 * r1;
+  n1 = n1 - cl * Dl * K * d2 * r1; n1 = n1 - cr * Dr * K * d1 * r2;
+  const double sol1 = n1 * jl_inv(den);
+  double n2 = root + Dr * d1 * r2;
+  n2 = n2 + cl * Dl * d2 * r1; n2 = n2 + cr * Dr * d1 * r2; n2 = n2 + Dl * K * d2 * r1;
+  n2 = n2 - cl * Dl * K * d2 * r1; n2 = n2 - cr * Dr * K * d1 * r2;
+  const double sol2 = n2 * den;                                                            /* :1187: multiplies */
+  const double br = (sol2 > 1.0 || sol2 < 0.0) ? sol1 : sol2;                              /* :1189-1193 */
+  *bc_right = br;
+  *bc_left = cl - Dr * d1 * jl_inv(Dl * d2) * (br - cr);                                   /* :1194 */
+}
 static inline double jl_sign(double x) { return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : x); }
 
 /* Base.Math.pow_body(x::Float64, n::Integer), Julia 1.10 base/math.jl (published algorithm). */
@@ -736,6 +778,11 @@ static int couple_step(member_t *m, scratch_t *sc) {
       for (int64_t j = 0; j < N; ++j) A[p * N + j] = dvol[j];
       rhs[p] = m->Mass0;
       A[q * N + p] = -1.0 * ScF; A[q * N + q] = +KD * ScF; rhs[q] = 0.0;
+    } else if (m->inner_bc == MBM_BC_LASAGA) {                                            /* :1196-1203 */
+      double bl, br;
+      lasaga_bc(m->cl[n1 - 2], m->cr[1], m->D_l, m->D_r, KD, dxl_if, dxr_if, rho[0], rho[1], &bl, &br);
+      A[p * N + p] = 1.0 * ScF; rhs[p] = bl * ScF;
+      A[q * N + q] = 1.0 * ScF; rhs[q] = br * ScF;
     } else {                                                                              /* Stefan :131-144, DCNI :108-118 */
       A[p * N + p] = 1.0 * ScF; rhs[p] = m->cl[n1 - 1] * ScF;
       A[q * N + q] = 1.0 * ScF; rhs[q] = m->cr[0] * ScF;
@@ -780,6 +827,8 @@ static int couple_step(member_t *m, scratch_t *sc) {
       /* sU + sVl*a + sVr*b = Mass0 ; -a + KD*b = 0 */
       b = (m->Mass0 - sU) / (sVl * KD + sVr);
       a = KD * b;
+    } else if (m->inner_bc == MBM_BC_LASAGA) {
+      lasaga_bc(m->cl[n1 - 2], m->cr[1], m->D_l, m->D_r, KD, dxl_if, dxr_if, rho[0], rho[1], &a, &b);
     } else {
       a = m->cl[n1 - 1];
       b = m->cr[0];
@@ -885,7 +934,7 @@ int mbm_couple_batch(const mbm_common *c, const mbm_couple_params *p, mbm_couple
   int rc = check_common(c);
   if (rc) return rc;
   if (!p || !io || c->cap_right < 3) return MBM_RC_BAD_ARG;
-  if (c->inner_bc < MBM_BC_FLUX || c->inner_bc > MBM_BC_DIRICHLET_HOLD) return MBM_RC_BAD_ARG;
+  if (c->inner_bc < MBM_BC_FLUX || c->inner_bc > MBM_BC_LASAGA) return MBM_RC_BAD_ARG;
   /* the same argument checks as the CUDA library's entry point (error behaviour is part of the ABI) */
   if (!p->Di || !p->rho || !p->t_tot || !p->CFL || !p->MRefin || !p->BCout || !p->resmin || !p->t_ar || !p->T_ar)
     return MBM_RC_BAD_ARG;
@@ -1003,7 +1052,7 @@ int mbm_couple_batch(const mbm_common *c, const mbm_couple_params *p, mbm_couple
 }
 
 int mbm_couple_flux_batch(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io *io) {
-  if (!c || (c->inner_bc != MBM_BC_FLUX && c->inner_bc != MBM_BC_DIRICHLET_HOLD)) return MBM_RC_BAD_ARG;
+  if (!c || (c->inner_bc != MBM_BC_FLUX && c->inner_bc != MBM_BC_DIRICHLET_HOLD && c->inner_bc != MBM_BC_LASAGA)) return MBM_RC_BAD_ARG;
   return mbm_couple_batch(c, p, io);
 }
 int mbm_couple_mb_batch(const mbm_common *c, const mbm_couple_params *p, mbm_couple_io *io) {

@@ -749,3 +749,25 @@ def test_streaming_fill_in_cutoff_changes_nothing(cuda_lib, monkeypatch):
     for m in range(3):
         for a, b in zip(ea.member(m), eb.member(m)):
             assert _relerr(a, b) < 1e-15
+
+
+def test_lasaga_interface_rows(oracle, cuda_lib):
+    """set_inner_bc_Lasaga! (src/functions.jl:1143-1206; exported, no shipped driver: the loop is DCGF's with this row function,
+    SURVEY 8(f) row 4): both interface values prescribed from the old neighbour values by the reference's closed form, restated
+    as shipped (sol2 multiplies by the denominator where sol1 divides, :1187).  Fixed and moving interface, planar /
+    cylindrical / spherical, against the oracle; the prescribed values are computed with the same operations in the same
+    order on both sides, so the interface values agree to the last bits"""
+    def mk(**kw):
+        p = d.pars_DCGF()
+        p.update(kind="lasaga", V_ip=0.0, Di=[4e-8, 5e-8], Cl_i=0.6, Cr_i=0.4, KD_ar=(1.8, 1.2), res=[60, 80], MRefin=5.0, n=1,
+                 t_tot=4e5, rho=[1.0, 1.1])
+        p.update(**kw)
+        return p
+    for n, V in ((1, 0.0), (3, 0.0), (2, 1e-8), (2, -1e-8)):
+        pars = [mk(n=n, V_ip=V), mk(n=n, V_ip=V, KD_ar=(0.7, 0.9), Cl_i=0.3, Cr_i=0.5, rho=[1.2, 1.0])]
+        eo, eg = run_both(pars, oracle, cuda_lib, 150)
+        assert np.all(eo.status == 0) and np.all(eo.it == 150), (eo.status, eo.it)
+        compare(eo, eg)
+        for m in range(2):
+            n1 = int(eo.res[m, 0])
+            assert eo.C_left[m, n1 - 1] == eg.C_left[m, n1 - 1] or _relerr(eo.C_left[m, :n1], eg.C_left[m, :n1]) < 1e-13

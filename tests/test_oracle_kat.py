@@ -158,3 +158,48 @@ def test_D1_material_law_prefix(oracle):
     assert abs(D_l - Dl_ref) <= 1e-4 * Dl_ref
     assert ens.Ri[0, 0] > p["Ri"]                                  # olivine grows on cooling
     assert abs((ens.Mass[0] - ens.Mass0[0]) / ens.Mass0[0]) < 2e-3
+
+
+def test_lasaga_rows_restated_as_shipped(oracle):
+    """set_inner_bc_Lasaga! (src/functions.jl:1143-1206, exported without a driver or a test: SURVEY 8(f) row 4).  The
+    oracle's prescribed interface values after one step against an independent restatement of the shipped closed form in
+    Python floats (same term order; sol2 times the denominator, :1187; selection :1189-1193), and the dense-LU path against
+    the structured one.  Finding recorded here: as shipped, neither root satisfies the equations quoted in the function's
+    own comment (Eq1: KD relation, Eq4: flux balance) - the residual of Eq1 is ~2e-2 at these parameters - so the
+    restatement is pinned to the formula, not to the physics (the reference's benchmark for it, B3, does not exist)."""
+    import math
+    from mbm_b200 import abi, drivers as d
+
+    def closed_form(cl, cr, Dl, Dr, K, d1, d2, r1, r2):
+        rad = (cl ** 2 * Dl ** 2 * K ** 2 * d2 ** 2 * r1 ** 2 - 2 * cl ** 2 * Dl ** 2 * K * d2 ** 2 * r1 ** 2
+               + cl ** 2 * Dl ** 2 * d2 ** 2 * r1 ** 2 + 2 * cl * cr * Dl * Dr * K ** 2 * d1 * d2 * r1 * r2
+               - 4 * cl * cr * Dl * Dr * K * d1 * d2 * r1 * r2 + 2 * cl * cr * Dl * Dr * d1 * d2 * r1 * r2
+               - 2 * cl * Dl ** 2 * K ** 2 * d2 ** 2 * r1 ** 2 + 2 * cl * Dl ** 2 * K * d2 ** 2 * r1 ** 2
+               + 2 * cl * Dl * Dr * K * d1 * d2 * r1 * r2 - 2 * cl * Dl * Dr * d1 * d2 * r1 * r2
+               + cr ** 2 * Dr ** 2 * K ** 2 * d1 ** 2 * r2 ** 2 - 2 * cr ** 2 * Dr ** 2 * K * d1 ** 2 * r2 ** 2
+               + cr ** 2 * Dr ** 2 * d1 ** 2 * r2 ** 2 - 2 * cr * Dl * Dr * K ** 2 * d1 * d2 * r1 * r2
+               + 2 * cr * Dl * Dr * K * d1 * d2 * r1 * r2 + 2 * cr * Dr ** 2 * K * d1 ** 2 * r2 ** 2
+               - 2 * cr * Dr ** 2 * d1 ** 2 * r2 ** 2 + Dl ** 2 * K ** 2 * d2 ** 2 * r1 ** 2
+               + 2 * Dl * Dr * K * d1 * d2 * r1 * r2 + Dr ** 2 * d1 ** 2 * r2 ** 2)
+        den = 2 * (Dr * d1 * r2 - Dr * K * d1 * r2)
+        rest = lambda h: h + cl * Dl * d2 * r1 + cr * Dr * d1 * r2 + Dl * K * d2 * r1 - cl * Dl * K * d2 * r1 - cr * Dr * K * d1 * r2
+        sol1 = rest(Dr * d1 * r2 - math.sqrt(rad)) / den
+        sol2 = rest(math.sqrt(rad) + Dr * d1 * r2) * den
+        br = sol1 if (sol2 > 1 or sol2 < 0) else sol2
+        return cl - Dr * d1 / (Dl * d2) * (br - cr), br
+
+    p = d.pars_DCGF()
+    p.update(kind="lasaga", V_ip=0.0, Di=[4e-8, 5e-8], Cl_i=0.6, Cr_i=0.4, KD_ar=(1.8, 1.2), res=[60, 80], MRefin=5.0, n=1,
+             t_tot=4e5, rho=[1.0, 1.1])
+    e0, _ = d.build_couple_ensemble([p], oracle)
+    e1 = e0.copy()
+    assert e1.run(oracle, max_steps=1) == 0 and e1.status[0] == 0
+    xl, cl, xr, cr = e0.member(0)
+    Dl, Dr, KD = (float(v) for v in e1.arrays["last"][0, :3])
+    a, b = closed_form(cl[-2], cr[1], Dl, Dr, KD, xl[-1] - xl[-2], xr[1] - xr[0], 1.0, 1.1)
+    assert abs(e1.C_left[0, 59] - a) < 1e-13 and abs(e1.C_right[0, 0] - b) < 1e-13
+    assert abs((a / (1 - a)) / (b / (1 - b)) - KD) > 1e-3          # the finding: Eq1 of the comment is not satisfied
+    es, ef = e0.copy(), e0.copy()
+    assert es.run(oracle, max_steps=200) == 0 and ef.run(oracle, max_steps=200, flags=abi.FLAG_SOLVER_FAITHFUL) == 0
+    for u, v in zip(es.member(0), ef.member(0)):
+        assert np.max(np.abs(u - v)) < 1e-11
