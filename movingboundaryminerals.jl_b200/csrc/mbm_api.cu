@@ -309,13 +309,27 @@ int v2_static_T(int ndim) {
   }
 #endif
 }
-void v2_plan(int capL, int capR, int nmax_hint, int smem_per_sm, int ndim, int *T2, int *kS) {
+// largest combined capacity of the tuned kernel with two CTAs per SM / with one CTA per SM (opt-in limit per block)
+void v2_capacities(int smem_per_sm, int smem_optin, int ndim, int *ks2, int *ks1) {
+  const int stat = v2_static_T<256>(ndim) + 64;          // the widest instantiation bounds the others
+  int a = ((smem_per_sm - 2 * 1024) / 2 - stat) / (4 * 8), b = (smem_optin - stat) / (4 * 8);
+  a -= a % 8; b -= b % 8;
+  *ks2 = a; *ks1 = b;
+}
+// members the host knows to be larger than two-per-SM allows (host buffers: largest n1 + n2 of the shard) but that fit one
+// CTA per SM with 9 * 256 nodes per phase still take the tuned kernel, at half the occupancy, instead of the general
+// kernel on a global workspace (an order of magnitude between the two)
+bool v2_one_cta_plan(int nmax_hint, int ks2, int ks1) {
+  if (nmax_hint <= 0 || getenv("MBM_V2_NO_ONE_CTA")) return false;
+  const int need = nmax_hint + nmax_hint / 4 + 2;
+  return need > ks2 && need <= ks1;
+}
+void v2_plan(int capL, int capR, int nmax_hint, int smem_per_sm, int smem_optin, int ndim, int *T2, int *kS) {
   int ks = capL + capR + 1;
   if (const char *e = getenv("MBM_KCAP")) { const int a = atoi(e); if (a >= 8 && a < ks) ks = a; }
-  const int stat = v2_static_T<256>(ndim) + 64;          // the widest instantiation bounds the others
-  const int per_cta = (smem_per_sm - 2 * 1024) / 2 - stat;
-  int ks_max = per_cta / (4 * 8);
-  ks_max -= ks_max % 8;
+  int ks_max = 0, ks_one = 0;
+  v2_capacities(smem_per_sm, smem_optin, ndim, &ks_max, &ks_one);
+  if (v2_one_cta_plan(nmax_hint, ks_max, ks_one)) ks_max = ks_one;
   if (ks > ks_max) ks = ks_max;
   // threads per member from the node counts when the host knows them (host buffers: largest n1 + n2 of the shard, with
   // room to grow by a quarter), else from the capacities; a member that outgrows 9*T nodes per phase is handed over
@@ -383,12 +397,24 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
   // the one that starts newton_solver from the member's previous root like the oracle does (mbm_oracle.c, regrid)
   const bool newton_warm = (flags & MBM_FLAG_NEWTON_WARM) != 0;
   const bool no_chain = newton_warm || getenv("MBM_NO_CHAIN");
-  bool use_v2 = couple_pv && !use_global && !no_chain && !getenv("MBM_NO_V2") && A.ndim >= 1 && A.ndim <= 3;
+  bool use_v2 = couple_pv && !no_chain && !getenv("MBM_NO_V2") && A.ndim >= 1 && A.ndim <= 3;
   int T2 = 256;
   if (use_v2) {
     int smem_sm = 0;
     CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
-    v2_plan(A.capL, A.capR, A.pad3_, smem_sm, A.ndim, &T2, &A.kcapL);
+    if (use_global) {
+      // capacities beyond the general kernel's shared-memory layout: the tuned kernel still takes the shard if the host
+      // knows that its members fit one CTA per SM
+      int k2 = 0, k1 = 0;
+      v2_capacities(smem_sm, maxOptin, A.ndim, &k2, &k1);
+      const int need = A.pad3_ + A.pad3_ / 4 + 2;
+      use_v2 = A.pad3_ > 0 && need <= k1 && !getenv("MBM_V2_NO_ONE_CTA") && !(flags & MBM_FLAG_FORCE_STREAMING);
+    }
+  }
+  if (use_v2) {
+    int smem_sm = 0;
+    CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+    v2_plan(A.capL, A.capR, A.pad3_, smem_sm, maxOptin, A.ndim, &T2, &A.kcapL);
     if (A.kcapL < 8) use_v2 = false;
   }
   if (couple_pv && !no_chain) {

@@ -787,3 +787,22 @@ def test_c4_full_length_members(oracle, cuda_lib):
     worst = compare(eo, eg, tol=TOL)
     print("c4 full length: max relative error", worst)
     assert np.max(np.abs(eg.Mass - eg.Mass0) / eg.Mass0) < 1e-9
+
+
+def test_members_beyond_two_per_sm_take_the_tuned_kernel(oracle, cuda_lib, monkeypatch):
+    """graded members of 3 500 - 4 000 nodes (more than two CTAs per SM hold, and capacities beyond the general kernel's
+    shared-memory layout): with host buffers the library knows the node counts and runs the tuned kernel with one CTA per
+    SM instead of the general kernel on a global workspace (growth members, and a resorption member whose right phase
+    jumps to 1 857 nodes at its first regrid - the reference's Newton solver does not converge much beyond 2 000).
+    Against the oracle, and against the global-memory path"""
+    pars = []
+    for V, res, r in ((1e-7, [1500, 2000], 0.5), (2e-7, [1500, 2000], 0.5), (-1e-7, [1300, 2000], 0.3)):
+        p = d.pars_MB_growth(); p.update(V_ip=V, res=res, Ri=[r, 1.0]); pars.append(p)
+    eo, eg = run_both(pars, oracle, cuda_lib, 60)
+    assert np.all(eo.status == 0), eo.status
+    assert eo.res[2, 1] > 1800
+    compare(eo, eg)
+    monkeypatch.setenv("MBM_V2_NO_ONE_CTA", "1")
+    eh, _ = d.build_couple_ensemble(pars, cuda_lib)
+    assert eh.run(cuda_lib, max_steps=60, flags=abi.FLAG_MASS_FINAL) == 0
+    compare(eo, eh)
