@@ -321,7 +321,9 @@ void v2_capacities(int smem_per_sm, int smem_optin, int ndim, int *ks2, int *ks1
 // kernel on a global workspace (an order of magnitude between the two)
 bool v2_one_cta_plan(int nmax_hint, int ks2, int ks1) {
   if (nmax_hint <= 0 || getenv("MBM_V2_NO_ONE_CTA")) return false;
-  const int need = nmax_hint + nmax_hint / 4 + 2;
+  // (the two-per-SM plan is only given up when the members as they ARE do not fit it: config 4's resorption members reach
+  //  2 887 of the 2 944 nodes two CTAs per SM hold and must stay two per SM)
+  const int need = nmax_hint + nmax_hint / 128 + 2;
   return need > ks2 && need <= ks1;
 }
 void v2_plan(int capL, int capR, int nmax_hint, int smem_per_sm, int smem_optin, int ndim, int *T2, int *kS) {
@@ -407,7 +409,7 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
       // knows that its members fit one CTA per SM
       int k2 = 0, k1 = 0;
       v2_capacities(smem_sm, maxOptin, A.ndim, &k2, &k1);
-      const int need = A.pad3_ + A.pad3_ / 4 + 2;
+      const int need = A.pad3_ + A.pad3_ / 128 + 2;
       use_v2 = A.pad3_ > 0 && need <= k1 && !getenv("MBM_V2_NO_ONE_CTA") && !(flags & MBM_FLAG_FORCE_STREAMING);
     }
   }
