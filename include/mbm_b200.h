@@ -302,6 +302,11 @@ double mbm_measure_dfma_tflops(int device);
  * Returns 0, or MBM_RC_CUDA.                                                                          */
 int mbm_stream_pass_counts(int device, uint64_t *fused_steps, uint64_t *twopass_steps, uint64_t *rows_without_fill_in);
 
+/* CUDA library only (oracle: 0).  Combined node capacity (left | free slot | right) the tuned resident kernel was launched
+ * with in the last couple call of this process, 0 if that call did not use it.  Two CTAs per SM hold up to ~2 944 nodes
+ * each, one CTA per SM up to ~6 500: tests use it to check which plan a shard took.                              */
+int mbm_last_tuned_capacity(void);
+
 #ifdef __cplusplus
 }
 #endif

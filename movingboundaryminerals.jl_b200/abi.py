@@ -106,7 +106,7 @@ ABI_SYMBOLS = [
     "mbm_simple_diff_batch", "mbm_couple_flux_batch", "mbm_couple_mb_batch",
     "mbm_stefan_xt_batch", "mbm_couple_batch", "mbm_create_grid", "mbm_calc_mass_vol",
     "mbm_last_kernel_seconds", "mbm_last_kernel_launches", "mbm_set_stream", "mbm_measure_dfma_tflops",
-    "mbm_validate_batch", "mbm_stream_pass_counts",
+    "mbm_validate_batch", "mbm_stream_pass_counts", "mbm_last_tuned_capacity",
 ]
 
 PKG_DIR = Path(__file__).resolve().parent
@@ -144,6 +144,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.mbm_measure_dfma_tflops.argtypes = [C.c_int]
     lib.mbm_validate_batch.restype = C.c_int
     lib.mbm_validate_batch.argtypes = [C.POINTER(ValidateArgs)]
+    lib.mbm_last_tuned_capacity.restype = C.c_int
     lib.mbm_stream_pass_counts.restype = C.c_int
     lib.mbm_stream_pass_counts.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     return lib

@@ -25,6 +25,7 @@ thread_local long long g_last_kernel_launches = 0;
 // last-call metrics readable from any host thread (bench / smoke): atomics, written once per call
 std::atomic<double> g_last_kernel_seconds_any{0.0};
 std::atomic<long long> g_last_kernel_launches_any{0};
+std::atomic<int> g_last_tuned_capacity{0};        // kcapL of the last launch of the tuned kernel (0: not used)
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -419,6 +420,7 @@ int launch_shard(mbm::KArgs A, int m0, int m1, int device, unsigned flags, cudaS
     v2_plan(A.capL, A.capR, A.pad3_, smem_sm, maxOptin, A.ndim, &T2, &A.kcapL);
     if (A.kcapL < 8) use_v2 = false;
   }
+  g_last_tuned_capacity.store(use_v2 ? A.kcapL : 0);
   if (couple_pv && !no_chain) {
     const int Tr = (use_v2 && T2 > T) ? T2 : T;
     A.recs = (double *)st->scratch((size_t)chunk * (size_t)Tr * mbm::REC_N * sizeof(double));
@@ -827,6 +829,7 @@ double mbm_measure_dfma_tflops(int device) {
   return best;
 }
 int64_t mbm_last_kernel_launches(void) { return g_last_kernel_launches_any; }
+int mbm_last_tuned_capacity(void) { return g_last_tuned_capacity.load(); }
 int mbm_stream_pass_counts(int device, uint64_t *fused_steps, uint64_t *twopass_steps, uint64_t *rows_without_fill_in) {
   int prev = 0;
   if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) return MBM_RC_CUDA;

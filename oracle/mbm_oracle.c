@@ -898,6 +898,7 @@ double mbm_last_kernel_seconds(void) { return 0.0; }
 int64_t mbm_last_kernel_launches(void) { return 0; }
 int mbm_set_stream(void *s) { (void)s; return 0; }
 double mbm_measure_dfma_tflops(int device) { (void)device; return 0.0; }
+int mbm_last_tuned_capacity(void) { return 0; }
 int mbm_stream_pass_counts(int device, uint64_t *fused_steps, uint64_t *twopass_steps, uint64_t *rows_without_fill_in) {
   (void)device; if (fused_steps) *fused_steps = 0; if (twopass_steps) *twopass_steps = 0;
   if (rows_without_fill_in) *rows_without_fill_in = 0;

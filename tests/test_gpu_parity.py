@@ -801,8 +801,24 @@ def test_members_beyond_two_per_sm_take_the_tuned_kernel(oracle, cuda_lib, monke
     eo, eg = run_both(pars, oracle, cuda_lib, 60)
     assert np.all(eo.status == 0), eo.status
     assert eo.res[2, 1] > 1800
+    assert cuda_lib.mbm_last_tuned_capacity() > 3500          # one CTA per SM
     compare(eo, eg)
     monkeypatch.setenv("MBM_V2_NO_ONE_CTA", "1")
     eh, _ = d.build_couple_ensemble(pars, cuda_lib)
     assert eh.run(cuda_lib, max_steps=60, flags=abi.FLAG_MASS_FINAL) == 0
+    assert cuda_lib.mbm_last_tuned_capacity() == 0
     compare(eo, eh)
+
+
+def test_config4_members_stay_two_per_sm(cuda_lib):
+    """BASELINE.json configs[3] through host buffers (the path bench.py's e2e takes): the resorption members reach 2 887
+    of the ~2 944 nodes that two CTAs per SM hold, so the shard must keep the two-per-SM plan at every call of a resumed
+    run - a capacity above that means one CTA per SM and half the throughput"""
+    from mbm_b200 import ensembles as E
+    pars = E.c4_mb_growth_resorption(64, res=1024, max_steps=10_000)
+    e, _ = d.build_couple_ensemble(pars, cuda_lib, cap_left=2048, cap_right=2560)
+    for _ in range(3):
+        assert e.run(cuda_lib, max_steps=100) == 0
+        cap = cuda_lib.mbm_last_tuned_capacity()
+        assert 2890 <= cap <= 3100, cap
+    assert np.all(e.status == 0) and int(np.max(e.res.sum(axis=1))) > 2800
