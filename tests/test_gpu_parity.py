@@ -822,3 +822,17 @@ def test_config4_members_stay_two_per_sm(cuda_lib):
         cap = cuda_lib.mbm_last_tuned_capacity()
         assert 2890 <= cap <= 3100, cap
     assert np.all(e.status == 0) and int(np.max(e.res.sum(axis=1))) > 2800
+
+
+def test_randomised_parity_sweep():
+    """tools/fuzz_parity.py with a fixed seed: 30 batches of random couple members (kind, geometry, velocity sign incl. 0,
+    radii, node counts up to 6 000 per phase, KD drift, outer boundary conditions, uniform / graded meshes, resident and
+    global-memory paths, split calls) through the CUDA library and the oracle - integers, status codes and the regrid
+    checksum equal, profiles within 1e-10"""
+    import subprocess, sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "tools" / "fuzz_parity.py"), "20261020", "30"], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "30 batches, 0 bad" in out.stdout
