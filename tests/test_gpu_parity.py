@@ -836,3 +836,16 @@ def test_randomised_parity_sweep():
                          text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert "30 batches, 0 bad" in out.stdout
+
+
+def test_randomised_parity_sweep_other_families():
+    """tools/fuzz_families.py with a fixed seed: 40 batches over the families the first sweep does not reach - the advective dt
+    rule of C1 / B4 / B5, fixed-interface flux / mass-balance / hold / Lasaga members (constant and Arrhenius diffusivities,
+    drifting KD, Dirichlet outer boundaries), Stefan sweeps - random sizes, geometries, step counts, split calls"""
+    import subprocess, sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "tools" / "fuzz_families.py"), "20261020", "40"], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "40 batches, 0 bad" in out.stdout
