@@ -70,6 +70,27 @@ def couple_batch():
     return fam, pars, eo, eg, tol, hashed
 
 
+def simple_batch():
+    """single-phase diffusion (Simple_Diff_1D_general / A1 / A2): random size, geometry, outer boundary conditions, CFL,
+    constant or Arrhenius diffusivity"""
+    M = int(rng.integers(1, 5))
+    fam = str(rng.choice(["sdg", "a1", "a2"]))
+    n = int(rng.integers(1, 4))
+    pars = []
+    for _ in range(M):
+        p = {"sdg": d.pars_SDG, "a1": d.pars_A1, "a2": d.pars_A2}[fam]()
+        bc = [int(rng.integers(0, 2)), int(rng.integers(0, 2))] if n == 1 else [0, int(rng.integers(0, 2))]
+        p.update(res=int(rng.integers(12, 3000)), n=n, BCout=bc, CFL=float(rng.uniform(0.3, 0.99)))
+        if fam != "sdg" and rng.random() < 0.3:            # Arrhenius diffusivity (Di == -1, functions.jl:1414-1417)
+            p.update(Di=-1.0, D0=2.75e-6, R=8.314472, Ea1=292880.0, T_ar=(1273.15, 1073.15))
+        pars.append(p)
+    arrh = any(p["Di"] == -1.0 for p in pars)
+    for p in pars:                                          # one call shares the gas constant
+        p.update(R=8.314472 if arrh else p["R"])
+    eo = d.build_simple_ensemble(pars)
+    return "simple-" + fam, pars, eo, eo.copy(), (2e-9 if arrh else 1e-10), False
+
+
 def stefan_batch():
     M = int(rng.integers(1, 5))
     pars = E.c2b_stefan_sweep(M, rank=int(rng.integers(0, 10_000)))
@@ -81,7 +102,8 @@ bad = 0
 t0 = time.time()
 for b in range(batches):
     try:
-        fam, pars, eo, eg, tol, hashed = stefan_batch() if rng.random() < 0.2 else couple_batch()
+        u_ = rng.random()
+        fam, pars, eo, eg, tol, hashed = stefan_batch() if u_ < 0.2 else simple_batch() if u_ < 0.4 else couple_batch()
     except (ValueError, RuntimeError) as e:
         print("skip batch", b, str(e)[:80]); continue
     steps = int(rng.integers(20, 200))
@@ -97,6 +119,10 @@ for b in range(batches):
         if eo.status[m] != 0:
             continue
         ok &= bool(np.array_equal(eo.res[m], eg.res[m]) and eo.it[m] == eg.it[m] and eo.node_steps[m] == eg.node_steps[m])
+        if fam.startswith("simple"):
+            nn_ = int(eo.res[m])
+            worst = max(worst, relerr(eo.C[m, :nn_], eg.C[m, :nn_]))
+            continue
         if hashed and fam != "b2":
             ok &= bool(eo.arrays["idx_hash"][m] == eg.arrays["idx_hash"][m])
         xl_o, cl_o, xr_o, cr_o = eo.member(m)
