@@ -59,13 +59,17 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period_ms=100):
+        # index: one GPU, or a comma-separated list: rank 0 of a multi-GPU run samples every GPU of the job in ONE nvidia-smi
+        # process.  Measured on the 8-GPU box: with one poller per rank (eight nvidia-smi processes at 10 Hz) every rank's
+        # kernels ran 11 % slower (85.3 ms per step instead of 76.7 ms, same clocks reported); one poller - at any period -
+        # costs nothing (profiles/README.md)
+        self.index, self.rows, self.proc, self.period_ms = index, [], None, period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", str(self.period_ms), "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -84,9 +88,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
+        self.per_gpu = {}
         for r in self.rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                self.per_gpu.setdefault(int(r[0]), []).append(float(r[1]))
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -225,8 +231,13 @@ def main():
         step_device()
     barrier()
     ns0 = int(dtens["node_steps"].sum().item())
-    sampler = ClockSampler(local)
-    sampler.start()
+    # one sampler per job: rank 0 watches every GPU of the run (ranks use GPUs 0 .. world-1 of the node)
+    period = int(os.environ.get("MBM_BENCH_CLOCK_MS", 200 if world > 1 else 100))
+    sampler = ClockSampler(",".join(str(g) for g in range(world)) if world > 1 else local, period)
+    if rank == 0 or os.environ.get("MBM_BENCH_SAMPLE_ALL_RANKS"):
+        if os.environ.get("MBM_BENCH_SAMPLE_ALL_RANKS"):
+            sampler = ClockSampler(local)
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -236,7 +247,7 @@ def main():
         launches += int(lib.mbm_last_kernel_launches())
     e1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler.proc else {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
     secs = e0.elapsed_time(e1) * 1e-3
     ns = int(dtens["node_steps"].sum().item()) - ns0
     bad = int((dtens["status"] != 0).sum().item())
@@ -246,11 +257,13 @@ def main():
     if world > 1:
         # every rank's own time, node-steps and SM clock (its own GPU, sampled during its timed region): shows whether a
         # max-over-ranks time above the single-GPU one is imbalance between the ranks' ensembles or a slower GPU
-        mine = torch.tensor([secs, float(ns), float(clocks["sm_mhz"] or 0.0)], device=dev, dtype=torch.float64)
+        mine = torch.tensor([secs, float(ns)], device=dev, dtype=torch.float64)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
+        per_gpu = getattr(sampler, "per_gpu", {})
         per_rank = {"ms_per_step": [1e3 * float(a[0].item()) / max(args.steps, 1) for a in allr],
-                    "node_steps": [float(a[1].item()) for a in allr], "sm_mhz": [float(a[2].item()) for a in allr]}
+                    "node_steps": [float(a[1].item()) for a in allr],
+                    "sm_mhz": [float(np.median(per_gpu[g])) if per_gpu.get(g) else None for g in range(world)]}
         dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
         dist.all_reduce(tns, op=dist.ReduceOp.SUM)
     secs_max, ns_all, bad_all = float(tsec.item()), float(tns[0].item()), int(tns[1].item())
