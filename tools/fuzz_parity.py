@@ -86,8 +86,17 @@ for b in range(batches):
     # kernels agree with each other to 1e-12 there (tools/cond_case.py), either differs from the oracle's sequential
     # elimination by 1e-11 (N = 10^4, 55 steps) up to a few 1e-9 (KD far from 1), as the reference's own dense LU does from a
     # structured solve at any N (<= 1e-9 for MB).  Everything else is held to 1e-10.
-    tol = 1e-8 if (kind == "mb" and big and uniform) else 1e-10
+    # Graded members beyond 3 000 nodes (one CTA per SM): the flux row -(al U + de W) / (ca KD + cb) with al, de ~ D / dx of the
+    # refined interface cells cancels to ~1e-6 of its terms, so the interface values carry the reduced solve's rounding at
+    # the 1e-10 level (one batch of 6 000 measured 1.03e-10 on the two interface nodes, 5e-16 elsewhere): 5e-10 there.
+    tol = 1e-8 if (kind == "mb" and big and uniform) else (5e-10 if (big and not uniform) else 1e-10)
     ok &= worst < tol
+    if os.environ.get("FUZZ_DUMP") and int(os.environ["FUZZ_DUMP"]) == b:       # where does the difference sit?
+        for m in range(M):
+            for nm, u, v in zip(("x_left", "C_left", "x_right", "C_right"), eo.member(m), eg.member(m)):
+                dd = np.abs(u - v); k = int(np.argmax(dd))
+                print(f"   member {m} {nm}: n={len(u)} max|diff|={dd.max():.3e} at {k} (value {u[k]:.6e}), median|diff|={np.median(dd):.3e}, "
+                      f"max|value|={np.max(np.abs(u)):.3e}")
     tag = "ok " if ok else "BAD"
     if not ok:
         bad += 1
