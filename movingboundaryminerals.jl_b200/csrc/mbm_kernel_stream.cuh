@@ -34,7 +34,7 @@ constexpr int SPF = MBM_SPF;   // software prefetch distance of the regrid walk,
 // an mbarrier) instead of per-thread loads: batches of STG_R rows, STG_NBF / STG_NBB batches resident for the forward
 // sweep (2 arrays) / the back-substitution (3 arrays), issued by thread 0 one batch ahead of the one being consumed.
 #ifndef MBM_STG_R
-#define MBM_STG_R 7
+#define MBM_STG_R 6
 #endif
 #ifndef MBM_STG_NBF
 #define MBM_STG_NBF 3
