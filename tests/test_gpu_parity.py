@@ -321,7 +321,7 @@ def test_streaming_interleaved_kernel(oracle, cuda_lib, kind):
 
 def test_streaming_kernel_row_batches(oracle, cuda_lib):
     """streaming kernel with columns of ~40 rows: the forward sweep and the back-substitution stage their rows through
-    shared memory in batches of 7 (cp.async.bulk + mbarrier), so this run takes several batches per pass and re-uses
+    shared memory in batches of 6 (cp.async.bulk + mbarrier), so this run takes several batches per pass and re-uses
     every staging buffer and barrier phase; node counts change on the way (growth and resorption)"""
     pars = []
     for V, res in ((1e-7, [4000, 6000]), (-1e-7, [4100, 5000]), (2e-7, [5000, 5001])):
