@@ -65,6 +65,10 @@ def couple_batch():
         p.update(n=pars[0]["n"], BCout=pars[0]["BCout"] if fam in ("b1", "b2") else p["BCout"])
     if fam == "b2":
         tol = 2e-9                                          # CUDA exp vs glibc exp: 1-ulp D differences feed dt
+    if fam == "lasaga":
+        tol = 1e-9       # the shipped closed form divides by 2 Dr dx1 rho2 (1 - KD): ill-conditioned where KD(t) passes near 1
+                         # (12 000 batches of all families: one Lasaga batch at 1.5e-10, the prescribed values themselves
+                         # are computed with identical operations on both sides)
     eo, _ = d.build_couple_ensemble(pars, ora)
     eg, _ = d.build_couple_ensemble(pars, lib)
     return fam, pars, eo, eg, tol, hashed
