@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MBM_ABI_VERSION 3
+#define MBM_ABI_VERSION 4
 
 /* ---- interface condition (which `set_inner_bc_*` the step uses) -------------------- */
 enum {
@@ -255,8 +255,15 @@ int mbm_calc_mass_vol(int32_t n_members, int32_t ndim, int32_t cap_left, int32_t
  *                     LinearIndices post-processing of :250-258) and the two trapezoidal integrals;
  *                     out = (int_Ray, int_model), relerr = |a - b| / max(|a|, |b|)  [isapprox, rtol]
  *   MBM_VAL_SMITH     test/test_B5.jl: smith (Benchmarks.jl:284-301, n = 1) against C_right;
- *                     out = (||Can - C_right||_2, max(||Can||_2, ||C_right||_2)), relerr = their ratio */
-enum { MBM_VAL_MASS_ERR = 0, MBM_VAL_RAYLEIGH = 1, MBM_VAL_SMITH = 2 };
+ *                     out = (||Can - C_right||_2, max(||Can||_2, ||C_right||_2)), relerr = their ratio
+ *   MBM_VAL_SPHERE    test/test_B1.jl and test/test_B2.jl: the eigenfunction series of diffusion in a sphere (Crank 1975,
+ *                     ch. 6.3) summed over 1000 terms as calc_sinus_sphere (Benchmarks.jl:82-99) and
+ *                     crank_time_transformation3 (:192-212) do, on x0 = [x_left; x_right] with the initial profile
+ *                     C0 = [C0_left; C0_right], against C = [C_left; C_right].  zeta[m] is the time-integrated
+ *                     diffusivity: D[1] * t for B1 (:94), trapezoidal_integration(tan, Dan) for B2 (:194-197; a
+ *                     1000-point scalar integral the host evaluates);
+ *                     out = (||Can - C||_2, max(||Can||_2, ||C||_2)), relerr = their ratio   [isapprox, rtol 1e-2] */
+enum { MBM_VAL_MASS_ERR = 0, MBM_VAL_RAYLEIGH = 1, MBM_VAL_SMITH = 2, MBM_VAL_SPHERE = 3 };
 typedef struct mbm_validate_args {
   int32_t abi_version;   /* MBM_ABI_VERSION                                                   */
   int32_t n_members, ndim, cap_left, cap_right, kind;
@@ -275,6 +282,8 @@ typedef struct mbm_validate_args {
   const double *t_tot;   /* [M]    SMITH: the time reached                                    */
   double *out;           /* [2,M]  see the kind                                               */
   double *relerr;        /* [M]                                                               */
+  const double *zeta;    /* [M]    SPHERE: time-integrated diffusivity (ABI 4)                */
+  const double *C0_left, *C0_right;   /* [cap_left,M], [cap_right,M]  SPHERE: initial profiles */
 } mbm_validate_args;
 int mbm_validate_batch(const mbm_validate_args *);
 

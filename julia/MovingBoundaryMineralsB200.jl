@@ -14,7 +14,7 @@ module MovingBoundaryMineralsB200
 using MovingBoundaryMinerals: scaling, rescale            # host-side pre/post steps stay the reference's own
 
 const LIB = get(ENV, "MBM_B200_LIB", joinpath(@__DIR__, "..", "movingboundaryminerals.jl_b200", "csrc", "libmbm_b200.so"))
-const ABI_VERSION = Int32(3)
+const ABI_VERSION = Int32(4)
 const BC_FLUX, BC_MB, BC_STEFAN, BC_HOLD, BC_LASAGA = Int32(1), Int32(2), Int32(3), Int32(4), Int32(5)
 const DT_FIND_DT, DT_ADVECTIVE, DT_STEFAN, DT_SIMPLE = Int32(0), Int32(1), Int32(2), Int32(3)
 const FLAG_RECORD, FLAG_MASS_FINAL = UInt32(0x0002), UInt32(0x0080)
@@ -51,8 +51,9 @@ struct ValidateArgs                # mbm_validate_args
     res::Ptr{Int64}; Ri::Ptr{Float64}; rho::Ptr{Float64}; Mass0::Ptr{Float64}; Ri0::Ptr{Float64}
     C0_r::Ptr{Float64}; KD0::Ptr{Float64}; Di_r::Ptr{Float64}; V_ip::Ptr{Float64}; t_tot::Ptr{Float64}
     out::Ptr{Float64}; relerr::Ptr{Float64}
+    zeta::Ptr{Float64}; C0_left::Ptr{Float64}; C0_right::Ptr{Float64}     # MBM_VAL_SPHERE (ABI 4)
 end
-const VAL_MASS_ERR = Int32(0); const VAL_RAYLEIGH = Int32(1); const VAL_SMITH = Int32(2)
+const VAL_MASS_ERR = Int32(0); const VAL_RAYLEIGH = Int32(1); const VAL_SMITH = Int32(2); const VAL_SPHERE = Int32(3)
 
 """
     rayleigh_gate(x_left, C_left, x_right, C_right, res, Ri, Ri0, C0_r_end, KD0; n)
@@ -66,7 +67,7 @@ function rayleigh_gate(x_left, C_left, x_right, C_right, res, Ri, Ri0, C0_r_end,
         va = Ref(ValidateArgs(ABI_VERSION, M, n, size(x_left, 1), size(x_right, 1), VAL_RAYLEIGH, 0, 0,
                               pointer(x_left), pointer(C_left), pointer(x_right), pointer(C_right), pointer(res),
                               pointer(Ri), C_NULL, C_NULL, pointer(Ri0), pointer(C0_r_end), pointer(KD0),
-                              C_NULL, C_NULL, C_NULL, pointer(out), pointer(relerr)))
+                              C_NULL, C_NULL, C_NULL, pointer(out), pointer(relerr), C_NULL, C_NULL, C_NULL))
         rc = ccall((:mbm_validate_batch, LIB), Cint, (Ref{ValidateArgs},), va)
         rc == 0 || error("mbm_validate_batch failed with rc = $rc")
     end

@@ -11,7 +11,7 @@ from pathlib import Path
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 LAW_NONE, LAW_OLIVINE_MELT_D1 = 0, 1      # mbm_couple_params.law (examples/D1.jl:126-132)
 
 # interface conditions / dt rules / flags (include/mbm_b200.h)
@@ -87,7 +87,7 @@ class SimpleIO(C.Structure):
 
 
 # every symbol include/mbm_b200.h declares
-VAL_MASS_ERR, VAL_RAYLEIGH, VAL_SMITH = 0, 1, 2   # mbm_validate_args.kind
+VAL_MASS_ERR, VAL_RAYLEIGH, VAL_SMITH, VAL_SPHERE = 0, 1, 2, 3   # mbm_validate_args.kind
 
 
 class ValidateArgs(C.Structure):
@@ -97,7 +97,7 @@ class ValidateArgs(C.Structure):
         ("cap_right", C.c_int32), ("kind", C.c_int32), ("flags", C.c_uint32), ("device", C.c_int32),
         ("x_left", _dp), ("C_left", _dp), ("x_right", _dp), ("C_right", _dp), ("res", _i64p), ("Ri", _dp),
         ("rho", _dp), ("Mass0", _dp), ("Ri0", _dp), ("C0_r", _dp), ("KD0", _dp), ("Di_r", _dp), ("V_ip", _dp),
-        ("t_tot", _dp), ("out", _dp), ("relerr", _dp),
+        ("t_tot", _dp), ("out", _dp), ("relerr", _dp), ("zeta", _dp), ("C0_left", _dp), ("C0_right", _dp),
     ]
 
 

@@ -987,11 +987,12 @@ int mbm_calc_mass_vol(int32_t M, int32_t ndim, int32_t capL, int32_t capR, const
 int mbm_validate_batch(const mbm_validate_args *a) {
   if (!a || a->abi_version != MBM_ABI_VERSION) return MBM_RC_BAD_ARG;
   if (a->n_members < 0 || a->cap_left < 3 || a->cap_right < 3 || a->ndim < 1 || a->ndim > 3) return MBM_RC_BAD_ARG;
-  if (a->kind < MBM_VAL_MASS_ERR || a->kind > MBM_VAL_SMITH) return MBM_RC_BAD_ARG;
+  if (a->kind < MBM_VAL_MASS_ERR || a->kind > MBM_VAL_SPHERE) return MBM_RC_BAD_ARG;
   if (!a->x_left || !a->C_left || !a->x_right || !a->C_right || !a->res || !a->Ri || !a->out || !a->relerr) return MBM_RC_BAD_ARG;
   if (a->kind == MBM_VAL_MASS_ERR && (!a->rho || !a->Mass0)) return MBM_RC_BAD_ARG;
   if (a->kind == MBM_VAL_RAYLEIGH && (!a->Ri0 || !a->C0_r || !a->KD0)) return MBM_RC_BAD_ARG;
   if (a->kind == MBM_VAL_SMITH && (!a->KD0 || !a->Di_r || !a->V_ip || !a->t_tot || a->ndim != 1)) return MBM_RC_BAD_ARG;
+  if (a->kind == MBM_VAL_SPHERE && (!a->zeta || !a->C0_left || !a->C0_right)) return MBM_RC_BAD_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return MBM_RC_NO_DEVICE;
   if (a->device < 0 || a->device >= ndev) return MBM_RC_NO_DEVICE;
@@ -1014,6 +1015,9 @@ int mbm_validate_batch(const mbm_validate_args *a) {
   V.rho = st.in(a->rho, 2 * n); V.Mass0 = st.in(a->Mass0, n);
   V.Ri0 = st.in(a->Ri0, 2 * n); V.C0_r = st.in(a->C0_r, n); V.KD0 = st.in(a->KD0, n);
   V.Di_r = st.in(a->Di_r, n); V.V_ip = st.in(a->V_ip, n); V.t_tot = st.in(a->t_tot, n);
+  if (a->kind == MBM_VAL_SPHERE) {
+    V.zeta = st.in(a->zeta, n); V.C0_left = st.in(a->C0_left, n * capL); V.C0_right = st.in(a->C0_right, n * capR);
+  }
   V.out = st.outonly(a->out, 2 * n); V.relerr = st.outonly(a->relerr, n);
   int rc = st.rc;
   if (!rc) {

@@ -12,7 +12,7 @@ struct VArgs {
   int M, ndim, capL, capR, kind;
   const double *x_left, *C_left, *x_right, *C_right;
   const long long *res;
-  const double *Ri, *rho, *Mass0, *Ri0, *C0_r, *KD0, *Di_r, *V_ip, *t_tot;
+  const double *Ri, *rho, *Mass0, *Ri0, *C0_r, *KD0, *Di_r, *V_ip, *t_tot, *zeta, *C0_left, *C0_right;
   double *out, *relerr;
 };
 
@@ -85,6 +85,38 @@ __global__ void mbm_validate_kernel(const VArgs a) {
       o1 = acc;
       const double den = fmax(fabs(o0), fabs(o1));
       e = den > 0.0 ? fabs(o0 - o1) / den : 0.0;
+    } else if (a.kind == 3) {
+      // calc_sinus_sphere (Benchmarks.jl:82-99) / crank_time_transformation3 (:192-212) with zeta = time-integrated
+      // diffusivity, isapprox of test_B1.jl / test_B2.jl (norm-wise); the series stops where its exponential has underflowed
+      // to zero (every further term is an exact zero)
+      const double *c0l = a.C0_left + (size_t)m * a.capL, *c0r = a.C0_right + (size_t)m * a.capR;
+      const double zeta = a.zeta[m];
+      const int N = n1 + n2;
+      const double PI = 3.14159265358979323846;
+      const double L = xr[n2 - 1], iL2 = 1.0 / (L * L);
+      double sd = 0.0, sa = 0.0, sb = 0.0;
+      for (int i = 0; i < N; ++i) {
+        const double x = (i < n1) ? xl[i] : xr[i - n1];
+        const double c0 = (i < n1) ? c0l[i] : c0r[i - n1];
+        const double c = (i < n1) ? cl[i] : cr[i - n1];
+        double Can;
+        if (i == N - 1) Can = c0;
+        else {
+          double acc = c0;
+          for (int nt = 1; nt <= 1000; ++nt) {
+            const double ex = exp(-zeta * (double)(nt * nt) * (PI * PI) * iL2);
+            if (ex == 0.0) break;
+            const double sg = (nt & 1) ? -1.0 : 1.0;
+            if (i == 0) acc = acc + 2.0 * (sg * ex);
+            else acc = acc + 2.0 * L * (1.0 / (PI * x)) * sg * (1.0 / (double)nt) * sin((double)nt * PI * x * (1.0 / L)) * ex;
+          }
+          Can = acc + 1.0;
+        }
+        sd += (Can - c) * (Can - c); sa += Can * Can; sb += c * c;
+      }
+      o0 = sqrt(sd);
+      o1 = sqrt(fmax(sa, sb));
+      e = o1 > 0.0 ? o0 / o1 : 0.0;
     } else {
       // smith (Benchmarks.jl:284-301), isapprox of test_B5.jl (norm-wise)
       const double Ri1 = a.Ri[2 * (size_t)m], Dan = a.Di_r[m], tan_ = a.t_tot[m], Kan = a.KD0[m], R = a.V_ip[m];

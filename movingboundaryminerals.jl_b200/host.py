@@ -191,10 +191,13 @@ class CoupleEnsemble:
             raise RuntimeError(f"mbm_calc_mass_vol failed rc={rc}")
         return out
 
-    def validate(self, lib, kind, Ri0=None, C0_r=None, KD0=None, Di_r=None, V_ip=None, t_tot=None, device=0):
+    def validate(self, lib, kind, Ri0=None, C0_r=None, KD0=None, Di_r=None, V_ip=None, t_tot=None, device=0, zeta=None,
+                 C0_left=None, C0_right=None):
         """mbm_validate_batch on the ensemble's state: (out[M,2], relerr[M]).  kind = abi.VAL_MASS_ERR (calc_mass_err of
         calc_mass_vol against Mass0), abi.VAL_RAYLEIGH (test_C1.jl's gate; needs Ri0[M,2], C0_r[M], KD0[M]) or
-        abi.VAL_SMITH (test_B5.jl's gate, n = 1; needs KD0, Di_r, V_ip, t_tot [M], in the units of the state)."""
+        abi.VAL_SMITH (test_B5.jl's gate, n = 1; needs KD0, Di_r, V_ip, t_tot [M], in the units of the state) or
+        abi.VAL_SPHERE (test_B1.jl / test_B2.jl: sphere series; needs zeta [M] = time-integrated diffusivity and the initial
+        profiles C0_left [M, cap_left], C0_right [M, cap_right])."""
         a = self.arrays
         keep = []
         def dp(v):
@@ -208,6 +211,7 @@ class CoupleEnsemble:
         va.res = abi.i64ptr(a["res"]); va.Ri = abi.dptr(a["Ri"]); va.rho = abi.dptr(a["rho"]); va.Mass0 = abi.dptr(a["Mass0"])
         va.Ri0, va.C0_r, va.KD0, va.Di_r, va.V_ip, va.t_tot = dp(Ri0), dp(C0_r), dp(KD0), dp(Di_r), dp(V_ip), dp(t_tot)
         va.out, va.relerr = abi.dptr(out), abi.dptr(err)
+        va.zeta, va.C0_left, va.C0_right = dp(zeta), dp(C0_left), dp(C0_right)
         rc = lib.mbm_validate_batch(C.byref(va))
         if rc != 0:
             raise RuntimeError(f"mbm_validate_batch failed rc={rc}")

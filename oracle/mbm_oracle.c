@@ -1283,15 +1283,52 @@ static void validate_smith(const double *xr, const double *cr, int64_t n2, doubl
   *nref = sqrt(sa > sb ? sa : sb);
 }
 
+
+/* calc_sinus_sphere (src/Benchmarks.jl:82-99) / crank_time_transformation3 (:192-212) with zeta = time-integrated
+ * diffusivity, then isapprox as test/test_B1.jl / test_B2.jl (norm-wise).  Per node the terms are added in the reference's
+ * order nt = 1..1000; once exp(-zeta nt^2 pi^2 / L^2) has underflowed to zero every further term is an exact zero, so the
+ * loop stops there (bit-identical sum). */
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+static void validate_sphere(const double *xl, const double *cl, const double *c0l, int64_t n1, const double *xr,
+                            const double *cr, const double *c0r, int64_t n2, double zeta, double *o0, double *o1) {
+  const int64_t N = n1 + n2;
+  const double L = xr[n2 - 1], iL2 = jl_inv(L * L);
+  double sd = 0.0, sa = 0.0, sb = 0.0;
+  for (int64_t i = 0; i < N; ++i) {
+    const double x = (i < n1) ? xl[i] : xr[i - n1];
+    const double c0 = (i < n1) ? c0l[i] : c0r[i - n1];
+    const double c = (i < n1) ? cl[i] : cr[i - n1];
+    double Can;
+    if (i == N - 1) Can = c0;                                                              /* :97  C[end] = Cs */
+    else {
+      double acc = c0;
+      for (int nt = 1; nt <= 1000; ++nt) {
+        const double e = exp(-zeta * (double)(nt * nt) * (M_PI * M_PI) * iL2);
+        if (e == 0.0) break;
+        const double sg = (nt & 1) ? -1.0 : 1.0;
+        if (i == 0) acc = acc + 2.0 * (sg * e);                                            /* :94  C1 */
+        else acc = acc + 2.0 * L * jl_inv(M_PI * x) * sg * jl_inv((double)nt) * sin((double)nt * M_PI * x * jl_inv(L)) * e;   /* :93 */
+      }
+      Can = acc + 1.0;                                                                     /* :95-96 */
+    }
+    sd += (Can - c) * (Can - c); sa += Can * Can; sb += c * c;
+  }
+  *o0 = sqrt(sd);
+  *o1 = sqrt(sa > sb ? sa : sb);
+}
+
 int mbm_validate_batch(const mbm_validate_args *a) {
   if (!a || a->abi_version != MBM_ABI_VERSION) return MBM_RC_BAD_ARG;
   if (a->n_members < 0 || a->cap_left < 3 || a->cap_right < 3 || a->ndim < 1 || a->ndim > 3) return MBM_RC_BAD_ARG;
-  if (a->kind < MBM_VAL_MASS_ERR || a->kind > MBM_VAL_SMITH) return MBM_RC_BAD_ARG;
+  if (a->kind < MBM_VAL_MASS_ERR || a->kind > MBM_VAL_SPHERE) return MBM_RC_BAD_ARG;
   if (a->flags & MBM_FLAG_DEVICE_POINTERS) return MBM_RC_UNSUPPORTED;
   if (!a->x_left || !a->C_left || !a->x_right || !a->C_right || !a->res || !a->Ri || !a->out || !a->relerr) return MBM_RC_BAD_ARG;
   if (a->kind == MBM_VAL_MASS_ERR && (!a->rho || !a->Mass0)) return MBM_RC_BAD_ARG;
   if (a->kind == MBM_VAL_RAYLEIGH && (!a->Ri0 || !a->C0_r || !a->KD0)) return MBM_RC_BAD_ARG;
   if (a->kind == MBM_VAL_SMITH && (!a->KD0 || !a->Di_r || !a->V_ip || !a->t_tot || a->ndim != 1)) return MBM_RC_BAD_ARG;
+  if (a->kind == MBM_VAL_SPHERE && (!a->zeta || !a->C0_left || !a->C0_right)) return MBM_RC_BAD_ARG;
 #pragma omp parallel for schedule(dynamic, 16)
   for (int64_t m = 0; m < a->n_members; ++m) {
     const double *xl = a->x_left + m * a->cap_left, *cl = a->C_left + m * a->cap_left;
@@ -1308,6 +1345,9 @@ int mbm_validate_batch(const mbm_validate_args *a) {
         validate_rayleigh(xl, cl, n1, a->Ri0 + 2 * m, a->Ri[2 * m], a->C0_r[m], a->KD0[m], a->ndim, &o0, &o1);
         const double den = fabs(o0) > fabs(o1) ? fabs(o0) : fabs(o1);
         e = den > 0.0 ? fabs(o0 - o1) / den : 0.0;
+      } else if (a->kind == MBM_VAL_SPHERE) {
+        validate_sphere(xl, cl, a->C0_left + m * a->cap_left, n1, xr, cr, a->C0_right + m * a->cap_right, n2, a->zeta[m], &o0, &o1);
+        e = o1 > 0.0 ? o0 / o1 : 0.0;
       } else {
         validate_smith(xr, cr, n2, a->Ri[2 * m], a->Di_r[m], a->t_tot[m], a->KD0[m], a->V_ip[m], &o0, &o1);
         e = o1 > 0.0 ? o0 / o1 : 0.0;

@@ -104,3 +104,61 @@ def test_reference_gates_on_full_runs_through_cuda(cuda_lib):
     assert np.all(err < 1e-4), err
     out, err = ens.validate(cuda_lib, abi.VAL_MASS_ERR)
     assert np.all(np.isfinite(err))
+
+
+def _sphere_inputs(ens0, ens, pars):
+    """zeta of every member as the reference's tests form it: D[1] * t for constant diffusivities (calc_sinus_sphere,
+    Benchmarks.jl:94), trapezoidal_integration(tan, Dan) over 1000 points for Arrhenius members
+    (crank_time_transformation3, :194-197); C0 = the initial profiles"""
+    a = ens.arrays
+    zeta = np.zeros(ens.M)
+    for m, p in enumerate(pars):
+        t = float(a["t"][m])
+        if p["Di"][0] == -1.0:
+            Tan = np.linspace(p["T_ar"][0], float(a["last"][m, 3]), 1000)
+            tan = np.linspace(0, t, 1000)
+            zeta[m] = B.trapezoidal_integration(tan, p["D0"][0] * np.exp(-p["Ea1"] * (1.0 / (p["R"] * Tan))))
+        else:
+            zeta[m] = float(a["Di"][m, 0]) * t
+    return dict(zeta=zeta, C0_left=ens0.arrays["C_left"], C0_right=ens0.arrays["C_right"])
+
+
+def test_oracle_sphere_gate_matches_numpy(oracle):
+    """MBM_VAL_SPHERE against tests/benchmarks_ref.py (calc_sinus_sphere / crank_time_transformation3 restated in numpy)
+    for B1 (constant D) and B2 (Arrhenius, time transformation) after 300 steps"""
+    for pars in ([d.pars_B1()], [d.pars_B2()]):
+        ens0, aux = d.build_couple_ensemble(pars, oracle)
+        ens = ens0.copy()
+        assert ens.run(oracle, max_steps=300) == 0 and ens.status[0] == 0
+        kw = _sphere_inputs(ens0, ens, pars)
+        out, err = ens.validate(oracle, abi.VAL_SPHERE, **kw)
+        xl, cl, xr, cr = ens.member(0)
+        xl0, cl0, xr0, cr0 = ens0.member(0)
+        x0, C0, Cm = np.concatenate([xl, xr]), np.concatenate([cl0, cr0]), np.concatenate([cl, cr])
+        p = pars[0]
+        if p["Di"][0] == -1.0:
+            Can, _ = B.crank_time_transformation3(C0, x0, p["T_ar"][0], float(ens.arrays["last"][0, 3]), p["Ea1"], p["R"],
+                                                  p["D0"][0], float(ens.t[0]), 1000)
+        else:
+            _, Can = B.calc_sinus_sphere(x0, C0, p["Di"][0], float(ens.t[0]), 1000)
+        ok, rel = B.isapprox(Can, Cm, 1e-2)
+        assert abs(err[0] - rel) < 1e-9 * max(rel, 1e-3), (err[0], rel)
+
+
+@pytest.mark.gpu
+def test_cuda_sphere_gate_matches_oracle_and_holds_on_full_runs(oracle, cuda_lib):
+    """the same state through both libraries; then test/test_B1.jl and test/test_B2.jl (rtol 1e-2) on the full runs through
+    the CUDA path (3 427 and 1 466 steps), decided by the library from the final state"""
+    for pars in ([d.pars_B1()], [d.pars_B2()]):
+        ens0, aux = d.build_couple_ensemble(pars, oracle)
+        ens = ens0.copy()
+        assert ens.run(oracle, max_steps=300) == 0
+        kw = _sphere_inputs(ens0, ens, pars)
+        oo, eo_err = ens.validate(oracle, abi.VAL_SPHERE, **kw)
+        og, eg_err = ens.validate(cuda_lib, abi.VAL_SPHERE, **kw)
+        assert np.allclose(oo, og, rtol=1e-9, atol=0) and np.allclose(eo_err, eg_err, rtol=1e-9, atol=1e-15), (oo, og)
+        full0, _ = d.build_couple_ensemble(pars, cuda_lib)
+        full = full0.copy()
+        assert full.run(cuda_lib) == 0 and full.status[0] == 0
+        out, err = full.validate(cuda_lib, abi.VAL_SPHERE, **_sphere_inputs(full0, full, pars))
+        assert err[0] < 1e-2, err

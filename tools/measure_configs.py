@@ -23,13 +23,14 @@ def relerr(a, b):
     return 0.0 if den == 0 else float(np.max(np.abs(a - b)) / den)
 
 
-def run(name, gen, build, M, max_steps, n_check, flags=0, tol=1e-10, ints=True):
+def run(name, gen, build, M, max_steps, n_check, flags=0, tol=1e-10, ints=True, gate=None):
     cuda, ora = mbm_b200.load_cuda_library(), oracle_load.load()
     pars = gen(M)
     t0 = time.perf_counter()
     eg = build(cuda, pars)
     tb = time.perf_counter() - t0
     eo = build(ora, pars[:n_check])      # the same first members through the oracle
+    eg0 = eg.copy() if gate else None    # the initial state (the known-answer gates need the initial profiles)
     warm = eg.copy()                     # a throw-away copy takes the one-off costs of the first call (allocator pool, module load)
     assert warm.run(cuda, max_steps=2, flags=flags) == 0
     del warm
@@ -55,6 +56,8 @@ def run(name, gen, build, M, max_steps, n_check, flags=0, tol=1e-10, ints=True):
            "members_failed": int((eg.status != 0).sum()), "parity_members": n_check, "parity_max_relerr": worst,
            "parity_integers_exact": ok_int, "oracle_node_steps_per_s": int(eo.node_steps.sum()) / tc,
            "build_s": tb}
+    if gate:
+        out.update(gate(cuda, eg0, eg))
     print(json.dumps(out), flush=True)
     assert worst < tol, (name, worst)
     assert ok_int, name
@@ -71,8 +74,15 @@ def main():
         res.append(run("c2b: Stefan sweep, res [15 25]", E.c2b_stefan_sweep, lambda lib, P: d.build_stefan_ensemble(P, lib),
                        4096, 2000, 4, tol=1e-8, ints=False))
     if "c3" in which:
+        def sphere_gate(lib, e0, e1):
+            # test/test_B1.jl's gate (sphere series, rtol 1e-2) for every member of the sweep, evaluated on the device
+            t0 = time.perf_counter()
+            out, err = e1.validate(lib, abi.VAL_SPHERE, zeta=e1.arrays["Di"][:, 0] * e1.arrays["t"], C0_left=e0.arrays["C_left"],
+                                   C0_right=e0.arrays["C_right"])
+            return {"sphere_gate_max_relerr": float(np.max(err)), "sphere_gate_members_within_1e-2": int(np.sum(err < 1e-2)),
+                    "sphere_gate_s": time.perf_counter() - t0}
         res.append(run("c3: flux fixed interface, n=256/phase", lambda M: E.c3_flux_fixed(M, 256), lambda lib, P: d.build_couple_ensemble(P, lib)[0],
-                       16384, 1000, 4))
+                       16384, 1000, 4, gate=sphere_gate))
     if "c5" in which:
         res.append(run("c5: MB growth n=65536/phase MRefin=1 (global-memory variant)",
                        lambda M: E.c5_highres(M, 65536, max_steps=100),
