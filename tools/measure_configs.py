@@ -70,6 +70,25 @@ def main():
     if "c2a" in which:   # examples/C1.jl sweep, 4096 members, whole run (~18k steps each) is long: 2000 steps
         res.append(run("c2a: C1 MB/Rayleigh sweep, res [80 120]", E.c2a_rayleigh_sweep, lambda lib, P: d.build_couple_ensemble(P, lib)[0],
                        4096, 2000, 4))
+    if "c2a" in which or "c2afull" in which:
+        # the whole sweep run to t_tot (~18 000 steps per member), every member checked on the device against its own
+        # Rayleigh curve (test_C1.jl's rtol is 1e-4 at the shipped parameters, the sweep widens KD0 / Ri / CFL)
+        cuda = mbm_b200.load_cuda_library()
+        pars = E.c2a_rayleigh_sweep(4096)
+        ens, aux = d.build_couple_ensemble(pars, cuda)
+        t0 = time.perf_counter()
+        assert ens.run(cuda, max_steps=0) == 0
+        te = time.perf_counter() - t0
+        ks = cuda.mbm_last_kernel_seconds()
+        out, err = ens.validate(cuda, abi.VAL_RAYLEIGH, Ri0=np.array(aux["Ri0"]), C0_r=np.array([c[-1] for c in aux["C0_r"]]), KD0=aux["KD0"])
+        ok = ens.status == 0
+        r = {"config": "c2a full runs: C1 MB/Rayleigh sweep to t_tot, every member against its own Rayleigh curve (device-side gate)",
+             "members": 4096, "members_failed": int((~ok).sum()), "steps_min_max": [int(ens.it[ok].min()), int(ens.it[ok].max())],
+             "node_steps": int(ens.node_steps.sum()), "kernel_s": ks, "e2e_s": te, "node_steps_per_s_kernel": int(ens.node_steps.sum()) / ks,
+             "rayleigh_gate_max_relerr": float(np.max(err[ok])), "rayleigh_gate_median_relerr": float(np.median(err[ok])),
+             "rayleigh_gate_members_within_1e-4": int(np.sum(err[ok] < 1e-4)), "rayleigh_gate_members_within_5e-3": int(np.sum(err[ok] < 5e-3))}
+        print(json.dumps(r), flush=True)
+        res.append(r)
     if "c2b" in which:
         res.append(run("c2b: Stefan sweep, res [15 25]", E.c2b_stefan_sweep, lambda lib, P: d.build_stefan_ensemble(P, lib),
                        4096, 2000, 4, tol=1e-8, ints=False))
