@@ -40,5 +40,7 @@ def load():
         lib.mbm_oracle_pow_int.argtypes = [C.c_double, C.c_int64]
         lib.mbm_oracle_scan.restype = None
         lib.mbm_oracle_scan.argtypes = [dp, C.c_int64, dp, C.c_int, C.c_int]
+        lib.mbm_oracle_capture_next_system.restype = None
+        lib.mbm_oracle_capture_next_system.argtypes = [dp, dp, dp, C.c_int64, i64p]
         _lib = lib
     return _lib

@@ -657,6 +657,15 @@ static int interp2(const double *X1d, const double *Y1d, const double *Z, int nd
   return 0;
 }
 
+/* Capture hook of the conditioning report (tools/conditioning_report.py): when armed, the next step
+ * solved by either mode leaves its dense system (as the reference would hand it to `\`, functions.jl:1292), its
+ * right-hand side and the solution it computed in the caller's buffers.  Single-threaded use only (one member).     */
+static struct { double *A, *rhs, *sol; int64_t cap, *N; int armed; } g_capture;
+void mbm_oracle_capture_next_system(double *A, double *rhs, double *sol, int64_t cap, int64_t *N) {
+  g_capture.A = A; g_capture.rhs = rhs; g_capture.sol = sol; g_capture.cap = cap; g_capture.N = N;
+  g_capture.armed = (A && rhs && sol && N) ? 1 : 0;
+}
+
 static int couple_step(member_t *m, scratch_t *sc) {
   int rc;
   double V_ip = m->V_ip;
@@ -756,10 +765,18 @@ static int couple_step(member_t *m, scratch_t *sc) {
   double KD = m->KD;
   double dxl_if = m->xl[n1 - 1] - m->xl[n1 - 2], dxr_if = m->xr[1] - m->xr[0];
 
-  if (m->flags & MBM_FLAG_SOLVER_FAITHFUL) {
+  const int capturing = g_capture.armed && N <= g_capture.cap;
+  if ((m->flags & MBM_FLAG_SOLVER_FAITHFUL) || capturing) {
     /* dense N x N, rows overwritten exactly as the reference does, then LU */
     double *A = (double *)calloc((size_t)N * (size_t)N, sizeof(double));
     if (!A) return MBM_ERR_CAPACITY;
+    double *rhs_struct = NULL;
+    if (!(m->flags & MBM_FLAG_SOLVER_FAITHFUL)) {            /* capture beside the structured solve: work on a copy */
+      rhs_struct = rhs;
+      rhs = (double *)malloc((size_t)N * sizeof(double));
+      if (!rhs) { free(A); return MBM_ERR_CAPACITY; }
+      memcpy(rhs, rhs_struct, (size_t)N * sizeof(double));
+    }
     for (int64_t i = 0; i < N; ++i) {
       A[i * N + i] = dia[i];
       if (i > 0 && i != n1) A[i * N + i - 1] = sub[i];
@@ -789,12 +806,21 @@ static int couple_step(member_t *m, scratch_t *sc) {
     }
     if (m->BCout[0] == 1) { for (int64_t j = 0; j < N; ++j) A[j] = 0.0; A[0] = 1.0 * ScF; rhs[0] = Co_l1 * ScF; }   /* :1232-1236 */
     if (m->BCout[1] == 1) { for (int64_t j = 0; j < N; ++j) A[(N - 1) * N + j] = 0.0; A[(N - 1) * N + N - 1] = 1.0 * ScF; rhs[N - 1] = Co_rend * ScF; } /* :1237-1241 */
-    int lrc = solve_dense(A, rhs, N);                                                     /* :1292 */
-    free(A);
-    if (lrc) return MBM_ERR_NONFINITE;
-    memcpy(m->cl, rhs, (size_t)n1 * sizeof(double));                                      /* :1293-1294 */
-    memcpy(m->cr, rhs + n1, (size_t)n2 * sizeof(double));
-  } else {
+    if (capturing) {
+      memcpy(g_capture.A, A, (size_t)N * (size_t)N * sizeof(double));
+      memcpy(g_capture.rhs, rhs, (size_t)N * sizeof(double));
+      *g_capture.N = N;
+    }
+    if (rhs_struct) { free(A); free(rhs); rhs = rhs_struct; }
+    else {
+      int lrc = solve_dense(A, rhs, N);                                                   /* :1292 */
+      free(A);
+      if (lrc) return MBM_ERR_NONFINITE;
+      memcpy(m->cl, rhs, (size_t)n1 * sizeof(double));                                    /* :1293-1294 */
+      memcpy(m->cr, rhs + n1, (size_t)n2 * sizeof(double));
+    }
+  }
+  if (!(m->flags & MBM_FLAG_SOLVER_FAITHFUL)) {
     /* structured O(N) solve of the SAME linear system: both interface rows become identity rows
      * (which decouples the blocks), two right-hand sides U (FEM rhs, interface values 0) and
      * V (zero rhs, interface values 1); the interface condition is a 2x2 for (a,b) =
@@ -837,6 +863,11 @@ static int couple_step(member_t *m, scratch_t *sc) {
     for (int64_t i = 0; i < n2; ++i) m->cr[i] = U[n1 + i] + Vv[n1 + i] * b;
     m->cl[n1 - 1] = a;
     m->cr[0] = b;
+  }
+  if (capturing) {
+    memcpy(g_capture.sol, m->cl, (size_t)n1 * sizeof(double));
+    memcpy(g_capture.sol + n1, m->cr, (size_t)n2 * sizeof(double));
+    g_capture.armed = 0;
   }
   /* ---- regrid!, functions.jl:869-905 ------------------------------------------------------ */
   if (Fl_regrid == 1) {
