@@ -97,6 +97,59 @@ def pars_MB_growth():
                 dt_mode=abi.DT_FIND_DT, init="mb_growth")
 
 
+def pars_B6():
+    """examples/B6.jl:7-33: flux couple, growing sphere, KD(t) falling to half its initial value"""
+    Cl_i = 0.1
+    Cr_i = Cl_i / 50.0
+    return dict(kind="flux", Di=[0.001, 0.005], D0=[np.nan, np.nan], rho=[1.0, 1.0], Ri=[1.0, 10.0], Cl_i=Cl_i, Cr_i=Cr_i,
+                V_ip=5e-3, R=np.nan, Ea1=np.nan, Ea2=np.nan, t_tot=3e2, n=3, KD_ar=(Cl_i / Cr_i, Cl_i / Cr_i * 0.5),
+                T_ar=(1273.0, 1073.0), CFL=0.4, res=[100, 100], MRefin=5.0, BCout=[0, 0], scale=True,
+                dt_mode=abi.DT_FIND_DT, init="uniform")
+
+
+def pars_B7():
+    """examples/B7.jl:7-33: flux couple, resorption (V_ip < 0), KD(t); ~3e5 steps at CFL 0.005"""
+    Cl_i = 0.1
+    Cr_i = Cl_i / 20.0
+    return dict(kind="flux", Di=[0.001, 0.005], D0=[np.nan, np.nan], rho=[1.0, 1.0], Ri=[5.0, 10.0], Cl_i=Cl_i, Cr_i=Cr_i,
+                V_ip=-5e-3, R=np.nan, Ea1=np.nan, Ea2=np.nan, t_tot=3e2, n=3, KD_ar=(Cl_i / Cr_i, Cl_i / Cr_i * 0.5),
+                T_ar=(1273.0, 1073.0), CFL=0.005, res=[200, 250], MRefin=10.0, BCout=[0, 0], scale=True,
+                dt_mode=abi.DT_FIND_DT, init="uniform")
+
+
+def pars_C2():
+    """examples/C2.jl:8-34: B7's couple with the mass-balance row"""
+    p = pars_B7()
+    p.update(kind="mb", T_ar=(1273.15, 1073.15))
+    return p
+
+
+def pars_Flux_growth():
+    """examples/Diff_couple_Flux_growth.jl:8-34: flux couple, cylinder, resorption, KD(t) falling to 0.4 KD0"""
+    Cl_i = 0.5
+    Cr_i = Cl_i / 0.1
+    return dict(kind="flux", Di=[4e-7, 5e-8], D0=[np.nan, np.nan], rho=[1.0, 1.0], Ri=[0.5, 1.0], Cl_i=Cl_i, Cr_i=Cr_i,
+                V_ip=-1e-7, R=np.nan, Ea1=np.nan, Ea2=np.nan, t_tot=1e6, n=2, KD_ar=(Cl_i / Cr_i, Cl_i / Cr_i * 0.4),
+                T_ar=(1273.15, 923.15), CFL=0.3, res=[100, 150], MRefin=10.0, BCout=[0, 0], scale=True,
+                dt_mode=abi.DT_FIND_DT, init="uniform")
+
+
+def pars_DC_Flux():
+    """examples/Diff_couple_Flux.jl:7-33 (unscaled SI): fixed interface, Arrhenius diffusivities on a cooling path, KD(t);
+    initial condition :54-55"""
+    return dict(kind="flux", Di=[-1.0, -1.0], D0=[2.75e-6, 3.9e-7], rho=[1.0, 1.0], Ri=[0.0002, 0.0005], Cl_i=0.6,
+                Cr_i=0.3, V_ip=0.0, R=8.314472, Ea1=292879.6767, Ea2=360660.4018, t_tot=1e-3 * Myr2Sec, n=3,
+                KD_ar=(1.0, 0.7), T_ar=(1273.15, 973.15), CFL=0.5, res=[100, 150], MRefin=2.0, BCout=[0, 0],
+                scale=False, dt_mode=abi.DT_FIND_DT, init="mb_growth")
+
+
+def pars_DC_MB():
+    """examples/Diff_couple_MB.jl:7-33: the same couple with the mass-balance row"""
+    p = pars_DC_Flux()
+    p.update(kind="mb")
+    return p
+
+
 def pars_DCNI():
     """examples/Diff_couple_no_interaction.jl:7-34"""
     return dict(kind="hold", Di=[2.65e-18, 2.65e-18], D0=[np.nan, np.nan], rho=[1.0, 1.0], Ri=[0.0002, 0.0004],
@@ -264,6 +317,60 @@ def C1(lib=None, **over):
             o["n"], o["maxC"], o["KD0"])
 
 
+def B6(lib=None, **over):
+    """examples/B6.jl:142 -> (x_left, x_right, x0, Ri, Ri0, C_left, C_right, C0, C0_r, KD0, n, maxC)"""
+    p = pars_B6(); p.update(over)
+    o = run_couple(p, lib)
+    return (o["x_left"], o["x_right"], o["x0"], o["Ri"], o["Ri0"], o["C_left"], o["C_right"], o["C0"], o["C0_r"],
+            o["KD0"], o["n"], o["maxC"])
+
+
+def B7(lib=None, **over):
+    """examples/B7.jl:142 -> B6's tuple (as shipped ~3e5 steps: pass max_steps through run_couple for a prefix)"""
+    p = pars_B7(); p.update(over)
+    o = run_couple(p, lib)
+    return (o["x_left"], o["x_right"], o["x0"], o["Ri"], o["Ri0"], o["C_left"], o["C_right"], o["C0"], o["C0_r"],
+            o["KD0"], o["n"], o["maxC"])
+
+
+def C2(lib=None, **over):
+    """examples/C2.jl:144 -> (x_left, x_right, x0, Ri, Ri0, C_left, C_right, C0, C0_r, n, maxC, KD0)"""
+    p = pars_C2(); p.update(over)
+    o = run_couple(p, lib)
+    return (o["x_left"], o["x_right"], o["x0"], o["Ri"], o["Ri0"], o["C_left"], o["C_right"], o["C0"], o["C0_r"],
+            o["n"], o["maxC"], o["KD0"])
+
+
+def _couple_12(p, lib):
+    o = run_couple(p, lib, record=True)
+    return (o["x_left"], o["x_right"], o["dx1"], o["dx2"], o["x0"], o["res"], o["Ri"], o["C_left"], o["C_right"],
+            o["C0"], o["Mass"], o["Mass0"])
+
+
+def DC_Flux_growth(lib=None, **over):
+    """examples/Diff_couple_Flux_growth.jl:138 -> DCGF's 12-tuple"""
+    p = pars_Flux_growth(); p.update(over)
+    return _couple_12(p, lib)
+
+
+def DC_MB_growth(lib=None, **over):
+    """examples/Diff_couple_MB_growth.jl -> (x_left, x_right, dx1, dx2, x0, res, Ri, C_left, C_right, C0, Mass, Mass0)"""
+    p = pars_MB_growth(); p.update(over)
+    return _couple_12(p, lib)
+
+
+def DC_Flux(lib=None, **over):
+    """examples/Diff_couple_Flux.jl:130 -> (x_left, x_right, dx1, dx2, x0, res, Ri, C_left, C_right, C0)"""
+    p = pars_DC_Flux(); p.update(over)
+    return _couple_12(p, lib)[:10]
+
+
+def DC_MB(lib=None, **over):
+    """examples/Diff_couple_MB.jl:132 -> DCGF's 12-tuple"""
+    p = pars_DC_MB(); p.update(over)
+    return _couple_12(p, lib)
+
+
 def DCNI(lib=None, **over):
     """examples/Diff_couple_no_interaction.jl -> (x_left, x_right, x0, C_left, C_right, C0, Cini_l, Cini_r,
     nmodes_l, nmodes_r, Amp_l, Amp_r, Di, Ri, t)"""
@@ -280,6 +387,13 @@ def pars_SDG():
     """main_codes/Simple_Diff_1D_general.jl:6-31"""
     return dict(Di=2.65e-18, D0=2.75e-6, L=0.001, rho=2700.0, R=8.314472, Ea1=292880.0, t_tot=1e-4 * Myr2Sec, n=1,
                 res=100, CFL=0.99, BCout=[1, 1], T_ar=(1273.15, 923.15), init="sdg", Cinf=0.0, Cstart=4.0)
+
+
+def pars_Simple_Diff():
+    """examples/Simple_Diff.jl:7-36: SDG's column with the Arrhenius diffusivity (Di = -1) on a cooling path"""
+    p = pars_SDG()
+    p.update(Di=-1.0)
+    return p
 
 
 def pars_A1():
@@ -352,6 +466,13 @@ def SDG(lib=None, **over):
     Mass0 = float(np.cumsum(0.5 * np.diff(V) * (C0[:-1] + C0[1:]))[-1])
     del ens0
     return o["x"], o["C"], o["x0"], o["C0"], o["D"], o["t"], o["t_tot"], o["Mass"], Mass0
+
+
+def Simple_Diff(lib=None, **over):
+    """examples/Simple_Diff.jl:107 -> (x, C, x0, C0, D, t, t_tot)"""
+    p = pars_Simple_Diff(); p.update(over)
+    o = run_simple(p, lib)
+    return o["x"], o["C"], o["x0"], o["C0"], o["D"], o["t"], o["t_tot"]
 
 
 def A1(lib=None, **over):

@@ -63,12 +63,31 @@ def test_library_identity(cuda_lib):
     ("MBmain_kd_t", d.pars_DCGMB, 0),
     ("Fluxmain", d.pars_DCGF, 0),
     ("DCNI_hold_dirichlet", d.pars_DCNI, 0),
+    ("B6_flux_growth_kd_t", d.pars_B6, 0),
+    ("B7_flux_resorption_kd_t", d.pars_B7, 800),
+    ("C2_mb_resorption_kd_t", d.pars_C2, 800),
+    ("Fluxgrowth_cyl_kd_t", d.pars_Flux_growth, 800),
+    ("DCFlux_fixed_arrhenius_kd_t", d.pars_DC_Flux, 0),
+    ("DCMB_fixed_arrhenius_kd_t", d.pars_DC_MB, 0),
 ])
 def test_fixture_parity(oracle, cuda_lib, name, pars, steps):
     """every shipped couple fixture of SURVEY.md §B, first `steps` steps (0 = whole run)"""
     tol = 2e-9 if "arrhenius" in name else TOL   # CUDA exp vs glibc exp: 1-ulp D differences feed dt
     eo, eg = run_both([pars()], oracle, cuda_lib, steps)
     compare(eo, eg, tol=tol)
+    assert _relerr(eo.Mass, eg.Mass) < 1e-11
+
+
+@pytest.mark.parametrize("name,pars,steps", [
+    ("Fluxgrowth", d.pars_Flux_growth, 39531),          # examples/Diff_couple_Flux_growth.jl as shipped
+    ("C2", d.pars_C2, 410719),                           # examples/C2.jl as shipped (CFL 0.005): 12 s of oracle time
+])
+def test_whole_run_of_long_example_fixtures(oracle, cuda_lib, name, pars, steps):
+    """whole runs, not prefixes: every step's node counts, regrid indices and pchip branches (checksum) equal, profiles to
+    1e-10 after up to 4e5 steps (measured 2e-12 / 9e-13; examples/B7.jl, the flux twin of C2: tools/whole_run_examples.py)"""
+    eo, eg = run_both([pars()], oracle, cuda_lib, 0)
+    assert int(eg.it[0]) == steps and eg.status[0] == 0
+    compare(eo, eg)
     assert _relerr(eo.Mass, eg.Mass) < 1e-11
 
 
@@ -102,6 +121,14 @@ def test_simple_A1(oracle, cuda_lib):
     Can = sinusoid_profile(0.0, p["nmodes"], p["L"], p["Di"], eg.t[0], p["Amp"], eg.x[0, :500])
     ok, err = B.isapprox(Can, eg.C[0, :500], 1e-4)
     assert ok, err
+
+
+def test_simple_arrhenius_cooling(oracle, cuda_lib):
+    """examples/Simple_Diff.jl: SDG's column with D(T(t)) from the Arrhenius law (Di = -1, functions.jl:1415), whole run"""
+    eo, eg = d.build_simple_ensemble([d.pars_Simple_Diff()]), d.build_simple_ensemble([d.pars_Simple_Diff()])
+    assert eo.run(oracle, flags=abi.FLAG_MASS_FINAL) == 0 and eg.run(cuda_lib, flags=abi.FLAG_MASS_FINAL) == 0
+    compare(eo, eg, tol=2e-9, simple=True)        # CUDA exp vs glibc exp (1 ulp in D feeds dt)
+    assert _relerr(eo.t, eg.t) < 1e-13 and _relerr(eo.D, eg.D) < 1e-14 and _relerr(eo.Mass, eg.Mass) < 1e-9
 
 
 def test_simple_A2_prefix(oracle, cuda_lib):

@@ -87,12 +87,38 @@ def test_DCNI(oracle):
     ("Flux_main", d.pars_DCGF, 6, [151, 150], 1e-4),
     ("C1", d.pars_C1, 18050, [80, 120], 1e-6),
     ("B5", d.pars_B5, 2530, [100, 160], 1e-4),
+    ("B6", d.pars_B6, 2648, [100, 100], 2e-4),                     # examples/B6.jl: flux, growth, KD(t)
+    ("Flux_growth", d.pars_Flux_growth, 39531, [100, 167], 1e-4),  # examples/Diff_couple_Flux_growth.jl: resorption, KD(t)
+    ("DC_Flux", d.pars_DC_Flux, 268, [100, 150], 2e-3),            # examples/Diff_couple_Flux.jl: fixed, Arrhenius, KD(t)
+    ("DC_MB", d.pars_DC_MB, 268, [100, 150], 1e-12),               # examples/Diff_couple_MB.jl: the same with the MB row
 ])
 def test_fixture_matrix(oracle, name, pars, steps, res, mass_tol):
     o = d.run_couple(pars(), oracle)
     assert o["it"] == steps
     assert list(o["res"]) == res
     assert abs((o["Mass_final"] - o["Mass0"]) / o["Mass0"]) < mass_tol
+
+
+@pytest.mark.parametrize("pars", [d.pars_B7, d.pars_C2])
+def test_long_resorption_fixtures_prefix(oracle, pars):
+    """examples/B7.jl / C2.jl (~3e5 steps at CFL 0.005 as shipped): the first 3 000 steps - the right phase takes the nodes the
+    left one loses (regrid!, functions.jl:881-888), KD follows its history, the MB row conserves the mass, the flux row does not"""
+    o = d.run_couple(pars(), oracle, max_steps=3000)
+    assert o["it"] == 3000 and list(o["res"]) == [200, 399] and abs(o["t"] - 3.120633708260443) < 1e-12
+    err = abs((o["Mass_final"] - o["Mass0"]) / o["Mass0"])
+    assert err < (1e-8 if pars is d.pars_C2 else 1e-3) and (pars is d.pars_C2 or err > 1e-5)
+    assert 19.6 < o["last"][2] < 20.0                       # KD on its way from 20 to 10
+
+
+def test_example_drivers_return_the_reference_tuples(oracle):
+    """B6 / C2-style / Diff_couple_* / Simple_Diff drop-ins: tuple lengths and the entries the reference's scripts plot"""
+    r = d.B6(oracle)
+    assert len(r) == 12 and r[9] == 50.0 and r[10] == 3 and r[0].size == 100 and abs(r[3][0] - 2.5) < 1e-9   # Ri grew from 1 to 1 + V t
+    r = d.DC_MB(oracle)
+    assert len(r) == 12 and r[10].size == 268 and abs(r[10][-1] / r[11] - 1.0) < 1e-12
+    assert len(d.DC_Flux(oracle)) == 10
+    x, C, x0, C0, D, t, t_tot = d.Simple_Diff(oracle)
+    assert t == t_tot and x.size == 100 and C0[0] == 4.0 and 7.3e-23 < D < 7.5e-23            # D at 923.15 K
 
 
 def test_stefan_main(oracle):
