@@ -24,6 +24,13 @@ FIXTURES = {
     "MB_growth_resorption": (d.pars_MB_growth, 400),   # examples/Diff_couple_MB_growth.jl
     "DCGMB_main": (d.pars_DCGMB, 12),             # main_codes/Diff_couple_1D_general_MB.jl (whole run)
     "DCGF_main": (d.pars_DCGF, 6),                # main_codes/Diff_couple_1D_general_Flux.jl (whole run)
+    "B6_flux_growth_kdt": (d.pars_B6, 400),       # examples/B6.jl
+    "B7_flux_resorption_kdt": (d.pars_B7, 400),   # examples/B7.jl
+    "C2_mb_resorption_kdt": (d.pars_C2, 400),     # examples/C2.jl
+    "Flux_growth_kdt": (d.pars_Flux_growth, 400), # examples/Diff_couple_Flux_growth.jl
+    "DC_Flux_fixed_arrhenius": (d.pars_DC_Flux, 268),   # examples/Diff_couple_Flux.jl (whole run)
+    "DC_MB_fixed_arrhenius": (d.pars_DC_MB, 268),       # examples/Diff_couple_MB.jl (whole run)
+    "DCNI_hold": (d.pars_DCNI, 209),              # examples/Diff_couple_no_interaction.jl (whole run)
 }
 
 
