@@ -132,19 +132,22 @@ def test_simple_arrhenius_cooling(oracle, cuda_lib):
 
 
 def test_simple_A2_prefix(oracle, cuda_lib):
-    """examples/A2.jl (sphere, Neumann/Dirichlet), first 2000 steps"""
+    """examples/A2.jl (sphere, Neumann/Dirichlet): first 2000 steps, then the whole run (41 647 steps, measured 9e-14)"""
     eo = d.build_simple_ensemble([d.pars_A2()])
     eg = eo.copy()
     assert eo.run(oracle, max_steps=2000) == 0 and eg.run(cuda_lib, max_steps=2000) == 0
     compare(eo, eg, simple=True)
+    assert eo.run(oracle) == 0 and eg.run(cuda_lib) == 0 and int(eg.it[0]) == 41647
+    compare(eo, eg, simple=True)
 
 
 def test_stefan_main(oracle, cuda_lib):
-    """main_codes/Chemical_Stefan_problem_XT.jl (rho == 1), first 1500 steps: V comes from the solution, so
-    Ri and dt are value-level (1e-10), node counts and step counts must still agree exactly"""
+    """main_codes/Chemical_Stefan_problem_XT.jl (rho == 1), the whole run (9 293 steps): V comes from the solution, so
+    Ri and dt are value-level (1e-10), node counts and step counts must still agree exactly (measured 9e-14)"""
     eo = d.build_stefan_ensemble([d.pars_CSP()], oracle)
     eg = d.build_stefan_ensemble([d.pars_CSP()], cuda_lib)
-    assert eo.run(oracle, max_steps=1500) == 0 and eg.run(cuda_lib, max_steps=1500) == 0
+    assert eo.run(oracle) == 0 and eg.run(cuda_lib) == 0
+    assert int(eg.it[0]) == 9293 and eg.res[0].tolist() == [28, 25]
     assert np.array_equal(eo.status, eg.status) and np.array_equal(eo.res, eg.res) and np.array_equal(eo.it, eg.it)
     for a, b in zip(eo.member(0), eg.member(0)):
         assert _relerr(a, b) < 1e-9
