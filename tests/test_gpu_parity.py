@@ -59,6 +59,9 @@ def test_library_identity(cuda_lib):
     ("B4_flux_growth_sphere", d.pars_B4, 600),
     ("B5_flux_growth_planar", d.pars_B5, 600),
     ("C1_mb_growth_sphere", d.pars_C1, 600),
+    ("B1_flux_fixed_whole_run", d.pars_B1, 0),
+    ("B2_flux_arrhenius_whole_run", d.pars_B2, 0),
+    ("B4_flux_growth_sphere_whole_run", d.pars_B4, 0),
     ("MBgrowth_mb_resorption_cyl", d.pars_MB_growth, 400),
     ("MBmain_kd_t", d.pars_DCGMB, 0),
     ("Fluxmain", d.pars_DCGF, 0),
@@ -75,7 +78,9 @@ def test_fixture_parity(oracle, cuda_lib, name, pars, steps):
     tol = 2e-9 if "arrhenius" in name else TOL   # CUDA exp vs glibc exp: 1-ulp D differences feed dt
     eo, eg = run_both([pars()], oracle, cuda_lib, steps)
     compare(eo, eg, tol=tol)
-    assert _relerr(eo.Mass, eg.Mass) < 1e-11
+    # the final mass is one more value of the state: 1e-11 after the prefixes, the profiles' own bar after whole runs
+    # (B4: 18 050 steps of a flux row on an MRefin = 50 sphere, measured 4.9e-11)
+    assert _relerr(eo.Mass, eg.Mass) < (tol if "whole_run" in name else 1e-11)
 
 
 @pytest.mark.parametrize("name,pars,steps", [
