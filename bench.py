@@ -366,7 +366,12 @@ def main():
                 "hbm_view": {"bound": "hbm", "achieved": per_gpu * 32 * 1e-9, "peak": hbm, "unit": "GB/s",
                              "frac": per_gpu * 32 * 1e-9 / hbm, "bytes_per_node_step": 32,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                             "note": "resident kernel: state crosses HBM once per launch, not once per step"}}
+                             "note": "resident kernel: state crosses HBM once per launch, not once per step"},
+                # NOT measured in this run: counters of the same kernel on the same workload from the committed capture
+                "pipe_view_from_ncu_capture": {"fp64_pipe_cycles_active_pct": 38.6, "issue_slots_active_pct": 50.0,
+                                               "shared_memory_pipe_pct": 40.4, "warps_per_sm": 16,
+                                               "fp64_instructions_per_node_step": 110,
+                                               "source": "profiles/r02_ncu_v2kernel_summary.txt"}}
 
     # ---------------- CPU baseline (bounded sample, N = 1 only) ------------------------------------------------
     cpu = None
