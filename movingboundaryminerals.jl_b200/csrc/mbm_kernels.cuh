@@ -718,7 +718,12 @@ __device__ __forceinline__ int red_ix(int g) {
   constexpr int RPL = T / 32;
   return (RPL > 1) ? g + g / RPL : g;
 }
-template <int T, int NRHS = 2, bool SKEW = false>
+// EARLY: leave the cyclic reduction as soon as every lane's couplings are below 1e-25 of its (unit) diagonal - the remaining
+// levels would then change nothing (dg = 1, corrections below 1e-25 of the neighbours' values).  With 8 chunk rows per lane
+// the lane-level couplings are the 8th power of the chunk-level ones, themselves the ~9th power of the row-level decay
+// (<= 0.27 per row for the backward-Euler FEM rows at CFL <= 0.5), so for members of a few thousand nodes the vote passes
+// before the first level; anything else runs the full reduction.
+template <int T, int NRHS = 2, bool SKEW = false, bool EARLY = false>
 __device__ __forceinline__ void reduced_solve(double *rs, double *rd, double *ru, double *r0, double *r1) {
   constexpr int RPL = T / 32;
   const int lane = threadIdx.x;  // caller guarantees threadIdx.x < 32
@@ -767,6 +772,7 @@ __device__ __forceinline__ void reduced_solve(double *rs, double *rd, double *ru
   // parallel cyclic reduction over the 32 lanes (rows stay normalised)
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
+    if (EARLY && __all_sync(0xffffffffu, fabs(ps) < 1e-25 && fabs(pu) < 1e-25)) break;
     double ls = __shfl_up_sync(0xffffffffu, ps, d), lu = __shfl_up_sync(0xffffffffu, pu, d);
     double l0 = __shfl_up_sync(0xffffffffu, p0, d), l1 = __shfl_up_sync(0xffffffffu, p1, d);
     double hs = __shfl_down_sync(0xffffffffu, ps, d), hu = __shfl_down_sync(0xffffffffu, pu, d);
