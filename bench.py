@@ -33,7 +33,7 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
-TRAFFIC_BYTES_8192 = 605.6e6 + 736.5e6     # ncu (profiles/r02_ncu_v2kernel_summary.txt), see roofline.traffic below
+TRAFFIC_BYTES_8192 = 606.5e6 + 737.5e6     # ncu (profiles/r02_ncu_v2kernel_summary.txt), see roofline.traffic below
 sys.path.insert(0, str(ROOT))
 
 
@@ -368,9 +368,9 @@ def main():
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                              "note": "resident kernel: state crosses HBM once per launch, not once per step"},
                 # NOT measured in this run: counters of the same kernel on the same workload from the committed capture
-                "pipe_view_from_ncu_capture": {"fp64_pipe_cycles_active_pct": 38.6, "issue_slots_active_pct": 50.0,
-                                               "shared_memory_pipe_pct": 40.4, "warps_per_sm": 16,
-                                               "fp64_instructions_per_node_step": 110,
+                "pipe_view_from_ncu_capture": {"fp64_pipe_cycles_active_pct": 38.8, "issue_slots_active_pct": 50.2,
+                                               "shared_memory_pipe_pct": 40.3, "warps_per_sm": 16,
+                                               "fp64_instructions_per_node_step": 109,
                                                "source": "profiles/r02_ncu_v2kernel_summary.txt"}}
 
     # ---------------- CPU baseline (bounded sample, N = 1 only) ------------------------------------------------
