@@ -110,6 +110,17 @@ def build_ensemble(lib, args, rank):
     return ens
 
 
+def host_threads(ora):
+    """all the host cores this process may use, set explicitly: torchrun exports OMP_NUM_THREADS=1 to its ranks (libgomp
+    reads it when it is loaded), which would time the CPU legs on one thread while reporting the machine's core count.
+    Returns the thread count the OpenMP runtime confirms."""
+    try:
+        want = len(os.sched_getaffinity(0))
+    except AttributeError:
+        want = os.cpu_count() or 1
+    return int(ora.mbm_oracle_set_threads(int(os.environ.get("MBM_BENCH_CPU_THREADS", want))))
+
+
 def reference_arm(args):
     """oracle port of the reference's CPU algorithm on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", 0))
@@ -118,7 +129,7 @@ def reference_arm(args):
     from oracle import load as oracle_load
     from mbm_b200 import abi
     ora = oracle_load.load()
-    cores = os.cpu_count()
+    cores = host_threads(ora)
     a = argparse.Namespace(**vars(args))
     a.members_per_gpu = max(cores, 8)
     ens = build_ensemble(ora, a, 0)
@@ -378,6 +389,7 @@ def main():
     if world == 1 and not args.no_cpu:
         from oracle import load as oracle_load
         ora = oracle_load.load()
+        cpu_threads = host_threads(ora)
         a = argparse.Namespace(**vars(args))
         a.members_per_gpu = args.cpu_members
         ce = build_ensemble(ora, a, 0)
@@ -386,7 +398,7 @@ def main():
         t0 = time.perf_counter()
         ce.run(ora, max_steps=args.cpu_tsteps)
         tc = time.perf_counter() - t0
-        cpu = {"value": (int(ce.node_steps.sum()) - n0) / tc, "unit": "node-steps/s", "cores": os.cpu_count(),
+        cpu = {"value": (int(ce.node_steps.sum()) - n0) / tc, "unit": "node-steps/s", "cores": cpu_threads,
                "kind": "port",
                "sample": f"{args.cpu_members} members x {args.cpu_tsteps} time steps of the same ensemble, structured O(N) solve, "
                          f"OpenMP schedule(dynamic) over members, {tc:.1f} s"}

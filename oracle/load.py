@@ -42,5 +42,7 @@ def load():
         lib.mbm_oracle_scan.argtypes = [dp, C.c_int64, dp, C.c_int, C.c_int]
         lib.mbm_oracle_capture_next_system.restype = None
         lib.mbm_oracle_capture_next_system.argtypes = [dp, dp, dp, C.c_int64, i64p]
+        lib.mbm_oracle_set_threads.restype = C.c_int
+        lib.mbm_oracle_set_threads.argtypes = [C.c_int]
         _lib = lib
     return _lib

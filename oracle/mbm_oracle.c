@@ -922,6 +922,13 @@ static int couple_step(member_t *m, scratch_t *sc) {
 /* ------------------------------------------------------------------------------------------ */
 /* ABI: couple ensembles                                                                       */
 /* ------------------------------------------------------------------------------------------ */
+/* Threads of the OpenMP loops over members: launchers such as torchrun export OMP_NUM_THREADS=1 to their ranks, which
+ * libgomp reads when it is loaded - bench.py's CPU legs ask for the host's cores explicitly and report what they got. */
+int mbm_oracle_set_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+}
+
 int mbm_version(void) { return MBM_ABI_VERSION; }
 int mbm_device_count(void) { return 0; }
 const char *mbm_backend(void) { return "oracle-cpu"; }

@@ -51,3 +51,25 @@ def test_two_rank_sharding_matches_single_process(tmp_path, oracle):
     assert np.array_equal(np.concatenate([r0["it"], r1["it"]]), ens.it)
     assert r0["ns"][0] == r1["ns"][0] == float(ens.node_steps.sum())           # SUM over ranks
     assert r0["tmax"][0] == r1["tmax"][0] == 2.0                               # MAX over ranks
+
+
+def test_reference_arm_under_torchrun_uses_the_host_cores():
+    """`bench.py --impl reference` launched as the driver launches it for N > 1: rank 0 alone prints ONE line, and it runs on
+    all the host threads although torchrun exports OMP_NUM_THREADS=1 to its ranks (`cores` is what the OpenMP runtime confirms)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    env = dict(os.environ); env.pop("OMP_NUM_THREADS", None)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29541", str(root / "bench.py"), "--impl", "reference", "--gpus", "2",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
